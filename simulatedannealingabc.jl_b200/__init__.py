@@ -1,0 +1,15 @@
+"""sabc_b200 -- B200-native SABC population engine (hot path of SimulatedAnnealingABC.jl behind a C ABI).
+
+    import sabc_b200 as sb
+    res = sb.sabc(sb.models.gauss_mean(1.0), sb.Normal(0, 1), n_particles=1000, n_simulation=100_000)
+    sb.update_population(res, model, prior, n_simulation=50_000)
+"""
+from . import _lib, models  # noqa: F401
+from ._lib import SABCError, SABC_FLAG_NO_GRAPH, SABC_FLAG_TIME_KERNELS  # noqa: F401
+from .api import Engine, SABCresult, SABCstate, sabc, update_population  # noqa: F401
+from .distributions import Normal, Product, Uniform, product_distribution  # noqa: F401
+from .models import DeviceModel  # noqa: F401
+from .proposals import DifferentialEvolution, RandomWalk, StretchMove  # noqa: F401
+
+__all__ = ["sabc", "update_population", "SABCresult", "SABCstate", "Engine", "DeviceModel", "models", "Normal", "Uniform",
+           "product_distribution", "DifferentialEvolution", "StretchMove", "RandomWalk", "SABCError"]

@@ -1,0 +1,745 @@
+// engine.cu -- the SABC population engine behind the C ABI (include/sabc_b200.h).
+//
+// Restates, B200-first, initialization() and update_population!() of the reference
+// (src/SimulatedAnnealingABC.jl:151-227, 251-402): all particle state is structure-of-arrays FP64
+// in HBM, one population update is a fixed sequence of kernels whose control state (iteration
+// number, ε, accept counters, resampling trigger, history cursor) lives in device memory, so the
+// sequence is captured once in a CUDA graph and replayed without host round trips.
+#include "aux_kernels.cuh"
+#include "common.h"
+#include "nccl_dyn.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace sabc {
+
+// ---------------------------------------------------------------------------------------------
+// error text + model registry
+// ---------------------------------------------------------------------------------------------
+char* last_error_buf() { static thread_local char buf[1024] = {0}; return buf; }
+int set_error(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(last_error_buf(), 1024, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static std::mutex g_reg_mutex;
+static std::vector<ModelVTable>& registry() { static std::vector<ModelVTable> r; return r; }
+static void ensure_builtin_models() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto& r = registry();
+        r.push_back(ModelLaunchers<GaussMean>::vtable("gauss_mean"));
+        r.push_back(ModelLaunchers<GaussSample<1, 1>>::vtable("gauss_sample_d1s1"));
+        r.push_back(ModelLaunchers<GaussSample<1, 2>>::vtable("gauss_sample_d1s2"));
+        r.push_back(ModelLaunchers<GaussSample<2, 1>>::vtable("gauss_sample_d2s1"));
+        r.push_back(ModelLaunchers<GaussSample<2, 2>>::vtable("gauss_sample_d2s2"));
+        r.push_back(ModelLaunchers<Logistic>::vtable("logistic"));
+        r.push_back(ModelLaunchers<SirTauLeap>::vtable("sir_tauleap"));
+    });
+}
+const ModelVTable* find_model(const char* name) {
+    ensure_builtin_models();
+    std::lock_guard<std::mutex> lk(g_reg_mutex);
+    for (auto& m : registry()) if (std::strcmp(m.name, name) == 0) return &m;
+    return nullptr;
+}
+
+}  // namespace sabc
+
+using namespace sabc;
+
+// ---------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------
+struct MgScratch {   // multi-GPU resampling work space
+    DevBuf<unsigned long long> wall, F, tsum, toff, scalar;
+    DevBuf<int64_t> src;
+    DevBuf<double> sb;
+    DevBuf<int> flag;
+};
+
+struct sabc_engine {
+    MgScratch mg;
+    // configuration
+    int64_t N = 0, n_local = 0, offset = 0;
+    int D = 0, S = 0, n_eps = 1, algorithm = 0, proposal = 0;
+    double prop_par[2] = {0, 0}, v = 1.0, delta = 0.1;
+    int64_t resample = 0;
+    uint64_t seed = 0;
+    uint32_t flags = 0;
+    int device = 0, rank = 0, world = 1, n_sm = 148;
+    const ModelVTable* model = nullptr;
+    ModelPar mp{};
+    PriorSpec prior{};
+    cudaStream_t stream = nullptr;
+    NcclComm comm;
+
+    // device state
+    DevBuf<double> b_theta, b_u, b_rho, b_lp, b_ttheta, b_tu, b_tlp;
+    PopView pop{}, tmp{};
+    DevBuf<DevState> b_ds;
+    DevBuf<EcdfStat> b_ecdf;
+    EcdfStat h_ecdf[MAX_S];
+    std::vector<DevBuf<double>*> ecdf_bufs;
+    int top_doubles = 0;
+    DevBuf<unsigned long long> b_q, b_tile_sum, b_tile_off;
+    DevBuf<double> b_rho_part, b_scratch, b_rw_part, b_rw_sums, b_hist;
+    int64_t part_ld = 0, scratch_ld = 0, hist_cap = 0;
+    int grid_update = 0, grid_aux = 0, bps_update = 0;
+    size_t smem_update = 0;
+
+    // graph
+    cudaGraphExec_t graph_exec = nullptr;
+
+    // host mirror of SABCstate
+    bool initialised = false;
+    double eps[MAX_S] = {0};
+    int64_t n_simulation = 0, n_accept = 0, n_resampling = 0, n_population_updates = 0;
+    std::vector<double> eps_h, u_h, rho_h;
+    sabc_timing timing{};
+
+    ~sabc_engine() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        for (auto* b : ecdf_bufs) delete b;
+        comm.destroy();
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static int halves(const sabc_engine* e, int half, int64_t& act_off, int64_t& act_n, int64_t& ina_off, int64_t& ina_n) {
+    const int64_t h0 = e->n_local / 2;                               // :300-301 batch_1 = 1:(N÷2)
+    if (half == 0) { act_off = 0; act_n = h0; ina_off = h0; ina_n = e->n_local - h0; }
+    else { act_off = h0; act_n = e->n_local - h0; ina_off = 0; ina_n = h0; }
+    return 0;
+}
+
+static int free_ecdf(sabc_engine* e) {
+    for (auto* b : e->ecdf_bufs) delete b;
+    e->ecdf_bufs.clear();
+    return 0;
+}
+
+// Build the index levels of statistic j over knots already resident in `knots` (device, L entries).
+static int ecdf_attach(sabc_engine* e, int j, DevBuf<double>* knots, int64_t L, int top_max) {
+    EcdfStat& st = e->h_ecdf[j];
+    std::memset(&st, 0, sizeof st);
+    st.L = L; st.lev[0] = knots->p; st.cnt[0] = L; st.nlev = 1;
+    SABC_CUDA(cudaMemcpyAsync(&st.kmax, knots->p + (L - 1), sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    while (st.cnt[st.nlev - 1] > top_max) {
+        if (st.nlev >= ECDF_MAX_LEVELS) return set_error(SABC_ERR_INVALID, "ECDF table too large for %d index levels", ECDF_MAX_LEVELS);
+        const int64_t cnt = (st.cnt[st.nlev - 1] + ECDF_FANOUT - 1) / ECDF_FANOUT;
+        auto* b = new DevBuf<double>();
+        e->ecdf_bufs.push_back(b);
+        SABC_CUDA(b->alloc((size_t)cnt));
+        const int grid = (int)std::min<int64_t>((cnt + 255) / 256, 4096);
+        k_sample16<<<grid, 256, 0, e->stream>>>(st.lev[st.nlev - 1], cnt, b->p);
+        SABC_CUDA(cudaGetLastError());
+        st.lev[st.nlev] = b->p; st.cnt[st.nlev] = cnt; st.nlev++;
+    }
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int ecdf_finalize(sabc_engine* e) {
+    int off = 0;
+    for (int j = 0; j < e->S; ++j) { e->h_ecdf[j].top_off = off; off += (int)e->h_ecdf[j].cnt[e->h_ecdf[j].nlev - 1]; }
+    e->top_doubles = off;
+    SABC_CUDA(e->b_ecdf.ensure(MAX_S));
+    SABC_CUDA(cudaMemcpyAsync(e->b_ecdf.p, e->h_ecdf, sizeof(EcdfStat) * e->S, cudaMemcpyHostToDevice, e->stream));
+    e->smem_update = (size_t)off * sizeof(double);
+    int bps = 0;
+    SABC_CUDA(e->model->update_occupancy(e->proposal, e->smem_update, &bps));
+    if (bps < 1) return set_error(SABC_ERR_CUDA, "update kernel does not fit on an SM (smem %zu B)", e->smem_update);
+    e->bps_update = bps;
+    const int64_t groups = (e->n_local - e->n_local / 2 + CHUNK - 1) / CHUNK;
+    e->grid_update = (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)bps * e->n_sm));
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    return 0;
+}
+
+static int top_max_for(int S) { return std::max(64, std::min(2048, 6144 / S)); }
+
+// build_cdf for column j from `d_col` (n values on the device)   src/cdf_estimators.jl:23-44
+static int ecdf_build_column(sabc_engine* e, int j, const double* d_col, int64_t n, DevBuf<double>& keys,
+                             DevBuf<unsigned char>& cub_tmp, DevBuf<unsigned long long>& cnt) {
+    SABC_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), e->stream));
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 8192);
+    k_mark_positive<<<grid, 256, 0, e->stream>>>(d_col, n, keys.p, cnt.p);
+    SABC_CUDA(cudaGetLastError());
+    auto* knots = new DevBuf<double>();
+    e->ecdf_bufs.push_back(knots);
+    SABC_CUDA(knots->alloc((size_t)n + 2));
+    size_t tmp_bytes = 0;
+    SABC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys.p, knots->p + 1, (int64_t)n, 0, 64, e->stream));
+    SABC_CUDA(cub_tmp.ensure(tmp_bytes));
+    SABC_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp.p, tmp_bytes, keys.p, knots->p + 1, (int64_t)n, 0, 64, e->stream));
+    unsigned long long n_pos = 0;
+    SABC_CUDA(cudaMemcpyAsync(&n_pos, cnt.p, sizeof n_pos, cudaMemcpyDeviceToHost, e->stream));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    if (n_pos == 0) return set_error(SABC_ERR_NO_POSITIVE, "build_cdf: statistic %d has no positive prior distance", j + 1);
+    k_ecdf_ends<<<1, 1, 0, e->stream>>>(knots->p, (int64_t)n_pos);
+    SABC_CUDA(cudaGetLastError());
+    return ecdf_attach(e, j, knots, (int64_t)n_pos + 2, top_max_for(e->S));
+}
+
+static int launch_update_half(sabc_engine* e, int half) {
+    UpdateArgs a{};
+    a.pop = e->pop;
+    halves(e, half, a.act_off, a.act_n, a.ina_off, a.ina_n);
+    a.particle_base = (uint32_t)e->offset;
+    a.half = half; a.seed = e->seed; a.ds = e->b_ds.p; a.ecdf = e->b_ecdf.p;
+    a.rho_part = e->b_rho_part.p + (int64_t)half * e->S * e->part_ld;
+    a.part_ld = e->part_ld; a.n_eps = e->n_eps; a.top_doubles = e->top_doubles;
+    a.prop0 = e->prop_par[0]; a.prop1 = e->prop_par[1];
+    a.prior = e->prior; a.mp = e->mp;
+    if (a.act_n <= 0) return 0;
+    SABC_CUDA(e->model->launch_update(e->proposal, a, e->grid_update, e->smem_update, e->stream));
+    return 0;
+}
+
+static int launch_post1(sabc_engine* e, int decide) {
+    Post1Args a{};
+    a.ds = e->b_ds.p; a.rho_part = e->b_rho_part.p; a.part_ld = e->part_ld;
+    int64_t o, n0, n1, t0, t1;
+    halves(e, 0, o, n0, t0, t1); halves(e, 1, o, n1, t0, t1);
+    a.groups0 = (n0 + CHUNK - 1) / CHUNK; a.groups1 = (n1 + CHUNK - 1) / CHUNK;
+    a.scratch = e->b_scratch.p; a.scratch_ld = e->scratch_ld;
+    a.S = e->S; a.n_global = e->N; a.resample = e->resample; a.decide = decide;
+    k_post1<<<2 * e->S + 1, CHUNK, 0, e->stream>>>(a);
+    SABC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// resample_population on one GPU (:124-137).  force = 1 at initialization (:197).
+static int launch_resample_local(sabc_engine* e, int force) {
+    const int64_t n = e->n_local;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int g_tiles = (int)std::min<int64_t>(n_tiles, (int64_t)e->n_sm * 8);
+    const int g_grp = (int)std::min<int64_t>((n + CHUNK - 1) / CHUNK, (int64_t)e->n_sm * 8);
+    DevState* ds = e->b_ds.p;
+    k_weights<<<g_tiles, CHUNK, 0, e->stream>>>(e->pop, n, e->S, e->delta, ds, e->b_q.p, e->b_tile_sum.p, force);
+    k_scan_tiles<<<1, 1024, 0, e->stream>>>(e->b_tile_sum.p, n_tiles, e->b_tile_off.p, &ds->w_total, ds, force);
+    k_prefix<<<g_tiles, CHUNK, 0, e->stream>>>(e->b_q.p, n, e->b_tile_off.p, ds, force);
+    k_draw_gather<<<g_grp, CHUNK, 0, e->stream>>>(e->pop, e->tmp, n, e->D, e->S, e->b_q.p, e->seed, ds, force);
+    k_copyback<<<g_grp, CHUNK, 0, e->stream>>>(e->pop, e->tmp, n, e->D, e->S, ds, force);
+    SABC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// update_proposal!(RandomWalk)  src/proposals.jl:46-48,58-60
+static int launch_update_proposal(sabc_engine* e) {
+    if (e->proposal != PROP_RW) return 0;
+    const int64_t n = e->n_local, groups = (n + CHUNK - 1) / CHUNK;
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8);
+    const int npair = e->D * (e->D + 1) / 2;
+    DevState* ds = e->b_ds.p;
+    k_group_sums<<<grid, CHUNK, 0, e->stream>>>(e->pop.theta, e->pop.ld, n, e->D, e->b_rw_part.p, e->part_ld * 2);
+    k_treesum_cols<<<e->D, CHUNK, 0, e->stream>>>(e->b_rw_part.p, e->part_ld * 2, groups, e->b_scratch.p, e->scratch_ld, e->b_rw_sums.p);
+    k_rw_means<<<1, 32, 0, e->stream>>>(ds, e->b_rw_sums.p, e->D, e->N);
+    k_rw_cross_sums<<<grid, CHUNK, 0, e->stream>>>(e->pop.theta, e->pop.ld, n, e->D, ds, e->b_rw_part.p, e->part_ld * 2);
+    k_treesum_cols<<<npair, CHUNK, 0, e->stream>>>(e->b_rw_part.p, e->part_ld * 2, groups, e->b_scratch.p, e->scratch_ld, e->b_rw_sums.p);
+    k_rw_chol<<<1, 32, 0, e->stream>>>(ds, e->b_rw_sums.p, e->D, e->N, e->prop_par[0]);
+    SABC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_finish(sabc_engine* e) {
+    FinishArgs a{};
+    a.ds = e->b_ds.p; a.hist = e->b_hist.p; a.S = e->S; a.n_eps = e->n_eps; a.algorithm = e->algorithm;
+    a.n_global = e->N; a.v = e->v;
+    k_finish<<<1, 32, 0, e->stream>>>(a);
+    SABC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int kernels_per_iteration(const sabc_engine* e) { return 2 + 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1; }
+
+// one population update, single GPU: every launch is unconditional, the resampling kernels
+// return immediately unless the device-side trigger fired
+static int enqueue_iteration(sabc_engine* e) {
+    SABC_TRY(launch_update_half(e, 0));
+    SABC_TRY(launch_update_half(e, 1));
+    SABC_TRY(launch_post1(e, 1));
+    SABC_TRY(launch_resample_local(e, 0));
+    SABC_TRY(launch_update_proposal(e));
+    SABC_TRY(launch_finish(e));
+    return 0;
+}
+
+static int sync_state_from_device(sabc_engine* e, int64_t* n_rec_out) {
+    DevState h;
+    SABC_CUDA(cudaMemcpyAsync(&h, e->b_ds.p, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < e->n_eps; ++k) e->eps[k] = h.eps[k];
+    e->n_accept = h.n_accept; e->n_resampling = h.n_resampling;
+    if (n_rec_out) *n_rec_out = h.rec;
+    if (h.error_flag & 1) return set_error(SABC_ERR_NEG_DISTANCE, "Negative distances are not allowed!");
+    if (h.error_flag & 2) return set_error(SABC_ERR_UBAR_ZERO, "Division by zero - Mean u for a statistic <= eps()");
+    return 0;
+}
+
+static int append_history(sabc_engine* e, int64_t n_rec) {
+    if (n_rec <= 0) return 0;
+    const int w = e->n_eps + 2 * e->S;
+    std::vector<double> h((size_t)n_rec * w);
+    SABC_CUDA(cudaMemcpy(h.data(), e->b_hist.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r < n_rec; ++r) {
+        const double* rec = h.data() + r * w;
+        e->eps_h.insert(e->eps_h.end(), rec, rec + e->n_eps);
+        e->u_h.insert(e->u_h.end(), rec + e->n_eps, rec + e->n_eps + e->S);
+        e->rho_h.insert(e->rho_h.end(), rec + e->n_eps + e->S, rec + w);
+    }
+    return 0;
+}
+
+static int ensure_hist(sabc_engine* e, int64_t n_rec) {
+    const int w = e->n_eps + 2 * e->S;
+    if (n_rec > e->hist_cap) { SABC_CUDA(e->b_hist.alloc((size_t)n_rec * w)); e->hist_cap = n_rec; }
+    return 0;
+}
+
+// Host-side plan of the surplus exchange of the multi-GPU resampling.  The selected particles of rank g occupy the
+// global slots [C_g, C_g + c_g) (C = exclusive prefix of counts); rank d owns the slots [d n, (d+1) n).
+extern "C" int sabc_mg_exchange_plan(const int64_t* counts, int32_t world, int64_t n_local, int32_t me, int64_t* send_off,
+                                     int64_t* send_cnt, int64_t* recv_off, int64_t* recv_cnt) {
+    if (!counts || world < 1 || me < 0 || me >= world) return set_error(SABC_ERR_INVALID, "bad exchange-plan argument");
+    std::vector<int64_t> C(world + 1, 0);
+    for (int g = 0; g < world; ++g) { if (counts[g] < 0) return set_error(SABC_ERR_INVALID, "negative count"); C[g + 1] = C[g] + counts[g]; }
+    if (C[world] != n_local * world) return set_error(SABC_ERR_INVALID, "counts do not sum to the global particle number");
+    for (int d = 0; d < world; ++d) {          // what I send to d (d == me: the part I keep)
+        const int64_t lo = std::max(C[me], (int64_t)d * n_local), hi = std::min(C[me + 1], (int64_t)(d + 1) * n_local);
+        send_off[d] = hi > lo ? lo - C[me] : 0; send_cnt[d] = hi > lo ? hi - lo : 0;
+    }
+    for (int g = 0; g < world; ++g) {          // what I receive from g, and where it lands in my slice
+        const int64_t lo = std::max(C[g], (int64_t)me * n_local), hi = std::min(C[g + 1], (int64_t)(me + 1) * n_local);
+        recv_off[g] = hi > lo ? lo - (int64_t)me * n_local : 0; recv_cnt[g] = hi > lo ? hi - lo : 0;
+    }
+    return 0;
+}
+
+#include "multi_gpu.inl"
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int sabc_abi_version(void) { return SABC_ABI_VERSION; }
+const char* sabc_last_error(void) { return last_error_buf(); }
+
+int sabc_device_count(int* n) {
+    SABC_CUDA(cudaGetDeviceCount(n));
+    return 0;
+}
+
+int sabc_nccl_unique_id(void* out128) { return nccl_get_unique_id(out128); }
+
+int sabc_host_alloc(void** out, int64_t bytes) {
+    SABC_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+int sabc_host_free(void* p) {
+    if (p) SABC_CUDA(cudaFreeHost(p));
+    return 0;
+}
+
+int sabc_register_model(const void* vtable) {
+    if (!vtable) return set_error(SABC_ERR_INVALID, "null vtable");
+    ensure_builtin_models();
+    const ModelVTable* vt = (const ModelVTable*)vtable;
+    std::lock_guard<std::mutex> lk(g_reg_mutex);
+    for (auto& m : registry()) if (std::strcmp(m.name, vt->name) == 0) { m = *vt; return 0; }
+    registry().push_back(*vt);
+    return 0;
+}
+int sabc_model_count(void) { ensure_builtin_models(); return (int)registry().size(); }
+const char* sabc_model_name(int i) {
+    ensure_builtin_models();
+    return (i >= 0 && i < (int)registry().size()) ? registry()[i].name : nullptr;
+}
+int sabc_model_info(const char* name, int32_t* n_para, int32_t* n_stats) {
+    const ModelVTable* m = find_model(name);
+    if (!m) return set_error(SABC_ERR_INVALID, "unknown device model '%s'", name);
+    if (n_para) *n_para = m->n_para;
+    if (n_stats) *n_stats = m->n_stats;
+    return 0;
+}
+
+int sabc_create(sabc_engine** out, const sabc_config* c) {
+    if (!out || !c) return set_error(SABC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (!(c->algorithm == SABC_ALG_SINGLE_EPS || c->algorithm == SABC_ALG_MULTI_EPS))
+        return set_error(SABC_ERR_BAD_ALGORITHM, "Argument `algorithm` must be :multi_eps or :single_eps");
+    if (c->proposal < 0 || c->proposal > 2) return set_error(SABC_ERR_BAD_PROPOSAL, "unknown proposal %d", c->proposal);
+    if (c->proposal == SABC_PROP_RW && !(c->prop_par[0] > 0.0 && c->prop_par[0] <= 1.0))
+        return set_error(SABC_ERR_BAD_PROPOSAL, "Mixing parameter `β` must be between zero and one.");
+    if (!c->model_name) return set_error(SABC_ERR_INVALID, "model_name is null");
+    const ModelVTable* model = find_model(c->model_name);
+    if (!model) return set_error(SABC_ERR_INVALID, "unknown device model '%s'", c->model_name);
+    if (model->n_para != c->n_para || model->n_stats != c->n_stats)
+        return set_error(SABC_ERR_INVALID, "model '%s' has %d parameters and %d statistics, config says %d and %d",
+                         c->model_name, model->n_para, model->n_stats, c->n_para, c->n_stats);
+    if (c->n_para > MAX_D || c->n_stats > MAX_S || c->n_model_par > MAX_MODEL_PAR || c->n_model_par < 0)
+        return set_error(SABC_ERR_INVALID, "dimension limits exceeded");
+    const int world = c->world_size > 1 ? c->world_size : 1;
+    if (c->n_particles % world != 0) return set_error(SABC_ERR_INVALID, "n_particles must be divisible by world_size");
+    const int64_t n_local = c->n_particles / world;
+    if (n_local < 4) return set_error(SABC_ERR_INVALID, "need at least 4 particles per GPU (each half >= 2)");
+    if (c->n_particles > 0xffffffffLL) return set_error(SABC_ERR_INVALID, "n_particles exceeds 2^32-1");
+    if (c->resample <= 0) return set_error(SABC_ERR_INVALID, "resample must be positive");
+
+    int ndev = 0;
+    SABC_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return set_error(SABC_ERR_CUDA, "no CUDA device");
+    int dev = c->device;
+    if (dev < 0) SABC_CUDA(cudaGetDevice(&dev));
+    SABC_CUDA(cudaSetDevice(dev));
+
+    auto* e = new sabc_engine();
+    e->N = c->n_particles; e->n_local = n_local; e->rank = world > 1 ? c->rank : 0; e->world = world;
+    e->offset = (int64_t)e->rank * n_local;
+    e->D = c->n_para; e->S = c->n_stats; e->algorithm = c->algorithm; e->proposal = c->proposal;
+    e->n_eps = c->algorithm == SABC_ALG_MULTI_EPS ? c->n_stats : 1;
+    e->prop_par[0] = c->prop_par[0]; e->prop_par[1] = c->prop_par[1];
+    e->v = c->v; e->delta = c->delta; e->resample = c->resample; e->seed = c->seed; e->flags = c->flags;
+    if (e->flags & SABC_FLAG_TIME_KERNELS) e->flags |= SABC_FLAG_NO_GRAPH;
+    if (world > 1) e->flags |= SABC_FLAG_NO_GRAPH;
+    e->device = dev; e->model = model;
+    for (int k = 0; k < c->n_model_par; ++k) e->mp.v[k] = c->model_par[k];
+    e->prior.n = e->D;
+    for (int k = 0; k < e->D; ++k) {
+        e->prior.kind[k] = c->prior_kind[k]; e->prior.p0[k] = c->prior_par[2 * k]; e->prior.p1[k] = c->prior_par[2 * k + 1];
+        if (c->prior_kind[k] != SABC_PRIOR_UNIFORM && c->prior_kind[k] != SABC_PRIOR_NORMAL) {
+            delete e; return set_error(SABC_ERR_INVALID, "unknown prior kind %d", c->prior_kind[k]);
+        }
+    }
+    prior_prepare(e->prior);
+
+    auto fail = [&](int rc) { delete e; return rc; };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return fail(set_error(SABC_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    e->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_error(SABC_ERR_CUDA, "stream creation failed"));
+
+    const size_t n = (size_t)n_local;
+    cudaError_t ce = cudaSuccess;
+    auto A = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
+    A(e->b_theta.alloc(n * e->D)); A(e->b_u.alloc(n * e->S)); A(e->b_rho.alloc(n * e->S)); A(e->b_lp.alloc(n));
+    A(e->b_ttheta.alloc(n * e->D)); A(e->b_tu.alloc(n * e->S)); A(e->b_tlp.alloc(n));
+    A(e->b_ds.alloc(1)); A(e->b_ecdf.alloc(MAX_S));
+    A(e->b_q.alloc(n));
+    const int64_t n_tiles = ((int64_t)n + TILE - 1) / TILE;
+    A(e->b_tile_sum.alloc((size_t)n_tiles)); A(e->b_tile_off.alloc((size_t)n_tiles));
+    e->part_ld = ((int64_t)n + CHUNK - 1) / CHUNK + 1;
+    A(e->b_rho_part.alloc((size_t)2 * e->S * e->part_ld));
+    e->scratch_ld = e->part_ld / CHUNK + 8;
+    const int ncol = std::max(2 * e->S + 1, e->D * (e->D + 1) / 2 + e->D);
+    A(e->b_scratch.alloc((size_t)ncol * e->scratch_ld));
+    A(e->b_rw_part.alloc((size_t)(e->D * (e->D + 1) / 2) * e->part_ld * 2)); A(e->b_rw_sums.alloc(MAX_D * MAX_D));
+    if (ce != cudaSuccess) return fail(set_error(SABC_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(ce)));
+    if (cudaMemsetAsync(e->b_ds.p, 0, sizeof(DevState), e->stream) != cudaSuccess) return fail(set_error(SABC_ERR_CUDA, "memset failed"));
+    e->pop = PopView{e->b_theta.p, e->b_u.p, e->b_rho.p, e->b_lp.p, (int64_t)n};
+    e->tmp = PopView{e->b_ttheta.p, e->b_tu.p, nullptr, e->b_tlp.p, (int64_t)n};
+    e->grid_aux = e->n_sm * 8;
+
+    if (world > 1) {
+        if (!c->nccl_unique_id) return fail(set_error(SABC_ERR_INVALID, "world_size > 1 needs nccl_unique_id"));
+        int rc = e->comm.init(c->nccl_unique_id, e->rank, world);
+        if (rc) return fail(rc);
+    }
+    *out = e;
+    return 0;
+}
+
+int sabc_destroy(sabc_engine* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    delete e;
+    return 0;
+}
+
+int sabc_set_tuning(sabc_engine* e, double v, double delta, int64_t resample, int32_t proposal, const double* prop_par) {
+    if (!e || !prop_par) return set_error(SABC_ERR_INVALID, "null argument");
+    if (proposal < 0 || proposal > 2) return set_error(SABC_ERR_BAD_PROPOSAL, "unknown proposal %d", proposal);
+    if (proposal == SABC_PROP_RW && !(prop_par[0] > 0.0 && prop_par[0] <= 1.0))
+        return set_error(SABC_ERR_BAD_PROPOSAL, "Mixing parameter `β` must be between zero and one.");
+    if (resample <= 0) return set_error(SABC_ERR_INVALID, "resample must be positive");
+    e->v = v; e->delta = delta; e->resample = resample;       // v, δ are validated by sabc_update like the reference (:261-262)
+    e->proposal = proposal; e->prop_par[0] = prop_par[0]; e->prop_par[1] = prop_par[1];
+    if (e->top_doubles > 0) SABC_TRY(ecdf_finalize(e));       // occupancy / grid of the newly selected kernel; drops the graph
+    return 0;
+}
+
+int sabc_local_particles(sabc_engine* e, int64_t* n_local, int64_t* offset) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (n_local) *n_local = e->n_local;
+    if (offset) *offset = e->offset;
+    return 0;
+}
+
+// initialization()  src/SimulatedAnnealingABC.jl:151-227
+int sabc_init(sabc_engine* e) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    SABC_CUDA(cudaSetDevice(e->device));
+    const int64_t n = e->n_local;
+    DevState* ds = e->b_ds.p;
+    SABC_CUDA(cudaMemsetAsync(ds, 0, sizeof(DevState), e->stream));
+    k_begin<<<1, 1, 0, e->stream>>>(ds, 0, 1, 1);
+    SABC_TRY(ensure_hist(e, 4));
+    e->eps_h.clear(); e->u_h.clear(); e->rho_h.clear();
+    e->n_resampling = 0;
+
+    // prior sample + first simulations (:172-179), negative check (:185), Σρ for ρ_history[1] (:180)
+    InitArgs ia{};
+    ia.pop = e->pop; ia.n = n; ia.particle_base = (uint32_t)e->offset; ia.seed = e->seed; ia.ds = ds;
+    ia.rho_part = e->b_rho_part.p; ia.part_ld = e->part_ld; ia.prior = e->prior; ia.mp = e->mp;
+    const int64_t groups = (n + CHUNK - 1) / CHUNK;
+    SABC_CUDA(e->model->launch_init(ia, (int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), e->stream));
+    k_treesum_cols<<<e->S, CHUNK, 0, e->stream>>>(e->b_rho_part.p, e->part_ld, groups, e->b_scratch.p, e->scratch_ld,
+                                                  &ds->rho_sum[0][0]);
+    SABC_CUDA(cudaGetLastError());
+    if (e->world > 1) SABC_TRY(mg_allreduce_f64(e, &ds->rho_sum[0][0], e->S));
+    {
+        int err = 0;
+        SABC_CUDA(cudaMemcpyAsync(&err, &ds->error_flag, sizeof err, cudaMemcpyDeviceToHost, e->stream));
+        SABC_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->world > 1) SABC_TRY(mg_any_flag(e, &err));
+        if (err & 1) return set_error(SABC_ERR_NEG_DISTANCE, "Negative distances are not allowed!");
+    }
+
+    // build_cdf per statistic (:187) from the GLOBAL prior sample
+    free_ecdf(e);
+    {
+        DevBuf<double> keys, gathered;
+        DevBuf<unsigned char> cub_tmp;
+        DevBuf<unsigned long long> cnt;
+        SABC_CUDA(keys.alloc((size_t)e->N)); SABC_CUDA(cnt.alloc(1));
+        if (e->world > 1) SABC_CUDA(gathered.alloc((size_t)e->N));
+        for (int j = 0; j < e->S; ++j) {
+            const double* col = e->pop.rho + (int64_t)j * e->pop.ld;
+            if (e->world > 1) { SABC_TRY(mg_allgather_f64(e, col, gathered.p, n)); col = gathered.p; }
+            SABC_TRY(ecdf_build_column(e, j, col, e->N, keys, cub_tmp, cnt));
+        }
+    }
+    SABC_TRY(ecdf_finalize(e));
+
+    // u = G(ρ) (:190-192) + exact Σu
+    k_transform<<<(int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), CHUNK, e->smem_update, e->stream>>>(e->pop, n, e->S, e->b_ecdf.p, ds);
+    SABC_CUDA(cudaGetLastError());
+    // first resampling (:197), ε_0 (:200-204), history record 0 (:180,207-208)
+    if (e->world > 1) SABC_TRY(mg_reduce_iteration_sums(e));
+    k_decide<<<1, 32, 0, e->stream>>>(ds, e->S, e->N, e->resample);          // ū for the weights
+    SABC_CUDA(cudaGetLastError());
+    if (e->world > 1) SABC_TRY(mg_resample(e)); else SABC_TRY(launch_resample_local(e, 1));
+    k_force_flag<<<1, 1, 0, e->stream>>>(ds, 1);
+    SABC_TRY(launch_finish(e));
+    int64_t n_rec = 0;
+    SABC_TRY(sync_state_from_device(e, &n_rec));
+    SABC_TRY(append_history(e, n_rec));
+    // counters (:213-223)
+    e->n_simulation = e->N; e->n_accept = 0; e->n_population_updates = 0;
+    k_set_counters<<<1, 1, 0, e->stream>>>(ds, 0, e->n_resampling);
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    e->initialised = true;
+    return 0;
+}
+
+// update_population!()  src/SimulatedAnnealingABC.jl:251-402
+int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (!e->initialised) return set_error(SABC_ERR_STATE, "sabc_update before sabc_init / sabc_set_population");
+    if (!(e->v > 0.0)) return set_error(SABC_ERR_BAD_V, "Annealing speed `v` must be positive.");
+    if (!(e->delta > 0.0)) return set_error(SABC_ERR_BAD_DELTA, "Resamping intensity `δ` must be positive.");
+    SABC_CUDA(cudaSetDevice(e->device));
+    if (checkpoint_history < 1) checkpoint_history = 1;
+    const int64_t n_pop = n_simulation / e->N;                       // :275
+    e->timing = sabc_timing{};
+    if (n_pop <= 0) return 0;
+    DevState* ds = e->b_ds.p;
+    SABC_TRY(ensure_hist(e, n_pop / checkpoint_history + 2));
+    k_begin<<<1, 1, 0, e->stream>>>(ds, (long long)(e->n_population_updates + 1), (long long)n_pop, (long long)checkpoint_history);
+    SABC_CUDA(cudaGetLastError());
+    if (e->world > 1) SABC_TRY(launch_update_proposal_mg(e)); else SABC_TRY(launch_update_proposal(e));   // :284
+
+    cudaEvent_t ev0, ev1;
+    SABC_CUDA(cudaEventCreate(&ev0)); SABC_CUDA(cudaEventCreate(&ev1));
+    std::vector<cudaEvent_t> kev;
+    const bool time_kernels = (e->flags & SABC_FLAG_TIME_KERNELS) != 0;
+    int rc = 0;
+    if (e->world > 1) {
+        SABC_CUDA(cudaEventRecord(ev0, e->stream));
+        for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) rc = mg_iteration(e);
+        SABC_CUDA(cudaEventRecord(ev1, e->stream));
+    } else if (e->flags & SABC_FLAG_NO_GRAPH) {
+        SABC_CUDA(cudaEventRecord(ev0, e->stream));
+        for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) {
+            if (time_kernels) {
+                for (int half = 0; half < 2 && rc == 0; ++half) {
+                    cudaEvent_t a, b;
+                    SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b));
+                    SABC_CUDA(cudaEventRecord(a, e->stream));
+                    rc = launch_update_half(e, half);
+                    SABC_CUDA(cudaEventRecord(b, e->stream));
+                    kev.push_back(a); kev.push_back(b);
+                }
+                if (rc == 0) rc = launch_post1(e, 1);
+                if (rc == 0) rc = launch_resample_local(e, 0);
+                if (rc == 0) rc = launch_update_proposal(e);
+                if (rc == 0) rc = launch_finish(e);
+            } else {
+                rc = enqueue_iteration(e);
+            }
+        }
+        SABC_CUDA(cudaEventRecord(ev1, e->stream));
+    } else {
+        if (!e->graph_exec) {
+            cudaGraph_t graph = nullptr;
+            SABC_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_iteration(e);
+            cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            SABC_CUDA(ce);
+            ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            SABC_CUDA(ce);
+        }
+        SABC_CUDA(cudaEventRecord(ev0, e->stream));
+        for (int64_t ix = 0; ix < n_pop; ++ix) SABC_CUDA(cudaGraphLaunch(e->graph_exec, e->stream));
+        SABC_CUDA(cudaEventRecord(ev1, e->stream));
+    }
+    if (rc) return rc;
+    int64_t n_rec = 0;
+    rc = sync_state_from_device(e, &n_rec);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    e->timing.update_ms = ms;
+    e->timing.kernel_launches = 2 * n_pop;
+    e->timing.total_launches = (int64_t)kernels_per_iteration(e) * n_pop;
+    for (size_t k = 0; k + 1 < kev.size(); k += 2) {
+        float t = 0.f; cudaEventElapsedTime(&t, kev[k], kev[k + 1]); e->timing.kernel_ms += t;
+        cudaEventDestroy(kev[k]); cudaEventDestroy(kev[k + 1]);
+    }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (rc) return rc;
+    SABC_TRY(append_history(e, n_rec));
+    e->n_simulation += n_pop * e->N;                                 // :391
+    e->n_population_updates += n_pop;                                // :394
+    return 0;
+}
+
+int sabc_get_population(sabc_engine* e, double* theta, double* u, double* rho) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    SABC_CUDA(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->n_local;
+    if (theta) SABC_CUDA(cudaMemcpyAsync(theta, e->pop.theta, n * e->D * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (u) SABC_CUDA(cudaMemcpyAsync(u, e->pop.u, n * e->S * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (rho) SABC_CUDA(cudaMemcpyAsync(rho, e->pop.rho, n * e->S * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int sabc_set_population(sabc_engine* e, const double* theta, const double* u, const double* rho, const double* eps,
+                        const int64_t counters[4]) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (!theta || !u || !rho || !eps || !counters) return set_error(SABC_ERR_INVALID, "null argument");
+    if (e->top_doubles == 0) return set_error(SABC_ERR_STATE, "no ECDF tables: call sabc_init or sabc_set_ecdf for every statistic first");
+    SABC_CUDA(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->n_local;
+    SABC_CUDA(cudaMemcpyAsync(e->pop.theta, theta, n * e->D * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    SABC_CUDA(cudaMemcpyAsync(e->pop.u, u, n * e->S * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    SABC_CUDA(cudaMemcpyAsync(e->pop.rho, rho, n * e->S * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, (int64_t)n, e->D, e->prior);
+    for (int k = 0; k < e->n_eps; ++k) e->eps[k] = eps[k];
+    e->n_simulation = counters[0]; e->n_accept = counters[1]; e->n_resampling = counters[2]; e->n_population_updates = counters[3];
+    SABC_CUDA(cudaMemcpyAsync(&e->b_ds.p->eps[0], e->eps, sizeof(double) * e->n_eps, cudaMemcpyHostToDevice, e->stream));
+    k_set_counters<<<1, 1, 0, e->stream>>>(e->b_ds.p, e->n_accept, e->n_resampling);
+    SABC_CUDA(cudaGetLastError());
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    e->initialised = true;
+    return 0;
+}
+
+int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, double* eps, int64_t counters[4],
+                     int64_t n_simulation, int64_t checkpoint_history) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    cudaEvent_t a, b, c, d;
+    SABC_CUDA(cudaSetDevice(e->device));
+    SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b)); SABC_CUDA(cudaEventCreate(&c)); SABC_CUDA(cudaEventCreate(&d));
+    SABC_CUDA(cudaEventRecord(a, e->stream));
+    SABC_TRY(sabc_set_population(e, theta, u, rho, eps, counters));
+    SABC_CUDA(cudaEventRecord(b, e->stream));
+    SABC_TRY(sabc_update(e, n_simulation, checkpoint_history));
+    SABC_CUDA(cudaEventRecord(c, e->stream));
+    SABC_TRY(sabc_get_population(e, theta, u, rho));
+    SABC_TRY(sabc_get_state(e, eps, counters));
+    SABC_CUDA(cudaEventRecord(d, e->stream));
+    SABC_CUDA(cudaEventSynchronize(d));
+    float t1 = 0, t2 = 0;
+    cudaEventElapsedTime(&t1, a, b); cudaEventElapsedTime(&t2, c, d);
+    e->timing.h2d_ms = t1; e->timing.d2h_ms = t2;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d);
+    return 0;
+}
+
+int sabc_get_state(sabc_engine* e, double* eps, int64_t counters[4]) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (eps) for (int k = 0; k < e->n_eps; ++k) eps[k] = e->eps[k];
+    if (counters) { counters[0] = e->n_simulation; counters[1] = e->n_accept; counters[2] = e->n_resampling; counters[3] = e->n_population_updates; }
+    return 0;
+}
+int sabc_history_len(sabc_engine* e, int64_t* n_records) {
+    if (!e || !n_records) return set_error(SABC_ERR_INVALID, "null argument");
+    *n_records = (int64_t)(e->eps_h.size() / (size_t)e->n_eps);
+    return 0;
+}
+int sabc_get_history(sabc_engine* e, double* eps_h, double* u_h, double* rho_h) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (eps_h) std::memcpy(eps_h, e->eps_h.data(), e->eps_h.size() * sizeof(double));
+    if (u_h) std::memcpy(u_h, e->u_h.data(), e->u_h.size() * sizeof(double));
+    if (rho_h) std::memcpy(rho_h, e->rho_h.data(), e->rho_h.size() * sizeof(double));
+    return 0;
+}
+int sabc_get_ecdf(sabc_engine* e, int32_t stat, double* knots_out, int64_t* L) {
+    if (!e || stat < 0 || stat >= e->S || e->h_ecdf[stat].L == 0) return set_error(SABC_ERR_INVALID, "no such ECDF");
+    if (L) *L = e->h_ecdf[stat].L;
+    if (knots_out) {
+        SABC_CUDA(cudaSetDevice(e->device));
+        SABC_CUDA(cudaMemcpy(knots_out, e->h_ecdf[stat].lev[0], (size_t)e->h_ecdf[stat].L * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+int sabc_set_ecdf(sabc_engine* e, int32_t stat, const double* knots, int64_t L) {
+    if (!e || stat < 0 || stat >= e->S || !knots || L < 3) return set_error(SABC_ERR_INVALID, "bad ECDF argument");
+    SABC_CUDA(cudaSetDevice(e->device));
+    auto* b = new DevBuf<double>();
+    e->ecdf_bufs.push_back(b);
+    SABC_CUDA(b->alloc((size_t)L));
+    SABC_CUDA(cudaMemcpyAsync(b->p, knots, (size_t)L * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    SABC_TRY(ecdf_attach(e, stat, b, L, top_max_for(e->S)));
+    bool all = true;
+    for (int j = 0; j < e->S; ++j) all = all && e->h_ecdf[j].L > 0;
+    if (all) SABC_TRY(ecdf_finalize(e));
+    return 0;
+}
+int sabc_get_timing(sabc_engine* e, sabc_timing* out) {
+    if (!e || !out) return set_error(SABC_ERR_INVALID, "null argument");
+    *out = e->timing;
+    return 0;
+}
+int sabc_update_kernel_info(sabc_engine* e, int* grid, int* block, int* smem_bytes, int* blocks_per_sm) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (grid) *grid = e->grid_update;
+    if (block) *block = CHUNK;
+    if (smem_bytes) *smem_bytes = (int)e->smem_update;
+    if (blocks_per_sm) *blocks_per_sm = e->bps_update;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,408 @@
+// kernels.cuh -- the fused per-particle kernels of the SABC population update, templated on the
+// model plug-in and the proposal kind, plus the small device functions shared with the parity
+// hooks (accept rule, epsilon solvers, radix-256 tree sums).
+//
+// Reference path: the particle body of update_population! (src/SimulatedAnnealingABC.jl:308-331)
+// and the prior-sample loop of initialization() (:172-179).  One thread owns one particle; a CTA
+// of 256 threads owns one 256-particle group of the tree-sum spec.
+#pragma once
+#include "plugin.cuh"
+#include <cuda_runtime.h>
+
+namespace sabc {
+
+// Device-resident algorithm state: everything that changes between population updates lives
+// here, so one captured CUDA graph can be replayed for every iteration without host round trips.
+struct DevState {
+    // [u_hi, u_lo, n_acc_iter] and [r_hi, r_lo] are contiguous: each is one integer all-reduce on multi-GPU
+    unsigned long long u_hi[MAX_S], u_lo[MAX_S];   // exact Σu limbs of the running iteration
+    unsigned long long n_acc_iter;                 // accepts of the running iteration
+    unsigned long long r_hi[MAX_S], r_lo[MAX_S];   // exact Σu limbs of the resampled population
+    unsigned long long w_total;                    // Σ fixed-point weights (this GPU)
+    double eps[MAX_S];
+    double chol[MAX_D * MAX_D];                    // RandomWalk: Cholesky factor / sd
+    double ubar[MAX_S];                            // column means of u (before resampling)
+    double rho_sum[2][MAX_S];                      // tree sums of ρ per half
+    double mom[MAX_D + MAX_D * MAX_D];             // RandomWalk: means, centred cross products
+    long long t;                                   // global population-update number being executed
+    long long ix, n_pop, checkpoint, rec, last_cp; // position inside the current update() call
+    long long n_accept, n_resampling;
+    int resample_flag, error_flag;
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared device functions
+// ------------------------------------------------------------------------------------------------
+
+// Accept rule, src/SimulatedAnnealingABC.jl:318-324.  uo/un stride through column-major rows.
+SABC_HD bool accept_rule(int s, const double* uo, int64_t ldo, const double* un, int64_t ldn, const double* eps,
+                         int n_eps, double dlp, double log_factor, double U) {
+    double S = 0.0;
+    for (int j = 0; j < s; ++j) {
+        const double t = (uo[j * ldo] - un[j * ldn]) / eps[n_eps == 1 ? 0 : j];
+        S = (j == 0) ? t : S + t;
+    }
+    const double Lacc = (dlp + S) + log_factor;
+    return det_log(U) < Lacc;
+}
+
+// update_epsilon_single_eps, :92-95: root of ε² + v ε^{3/2} − ū² by monotone Newton on s = sqrt(ε)
+SABC_HD double eps_single(double ubar, double v) {
+    if (ubar <= 2.220446049250313e-16) return 0.0;
+    const double u2 = ubar * ubar;
+    double s = sqrt(ubar);
+    for (int it = 0; it < 64; ++it) {
+        const double s2 = s * s, s3 = s2 * s;
+        const double f = (s3 * s + v * s3) - u2;
+        const double fp = 4.0 * s3 + (3.0 * v) * s2;
+        const double sn = s - f / fp;
+        if (!(sn < s)) break;
+        s = sn;
+    }
+    return s * s;
+}
+
+SABC_HD double ipow(double x, int m) { double p = 1.0; for (int i = 0; i < m; ++i) p = p * x; return p; }
+SABC_HD double powhalf(double x, int m) { return (m & 1) ? sqrt(x) * ipow(x, (m - 1) / 2) : ipow(x, m / 2); }
+
+// update_epsilon_multi_eps, :100-117, component i.  Returns false if ū_i <= eps() (:107-109).
+SABC_HD bool eps_multi_one(const double* ubar, int n, int i, double v, double& eps_out) {
+    double cn = 1.0;
+    for (int k = 2; k <= n + 1; ++k) cn = cn * (double)(n + 1 + k) / (double)k;
+    const double ui = ubar[i];
+    if (ui <= 2.220446049250313e-16) return false;
+    double sumq = 0.0, prodq = 1.0;
+    for (int j = 0; j < n; ++j) {
+        const double q = ubar[j] / ui;
+        const double t = powhalf(q, n);
+        sumq = (j == 0) ? t : sumq + t;
+        prodq = (j == 0) ? q : prodq * q;
+    }
+    const double num = 1.0 + sumq;
+    const double den = ((cn * (double)(n + 1)) * powhalf(ui, n + 2)) * prodq;
+    double beta = 1.0 / ui;
+    for (int it = 0; it < 100; ++it) {
+        double g, dg;
+        if (fabs(beta) < 0.01) {
+            const double b2 = beta * beta;
+            g = 0.5 - beta * (1.0 / 12.0 - b2 * (1.0 / 720.0 - b2 * (1.0 / 30240.0)));
+            dg = -(1.0 / 12.0) + b2 * (1.0 / 240.0 - b2 * (1.0 / 6048.0));
+        } else {
+            const double t = det_exp(-beta), omt = 1.0 - t;
+            g = 1.0 / beta - t / omt;
+            dg = t / (omt * omt) - 1.0 / (beta * beta);
+        }
+        const double bn = beta - (g - ui) / dg;
+        const double diff = fabs(bn - beta);
+        beta = bn;
+        if (diff <= 4.0e-16 * fabs(bn)) break;
+    }
+    eps_out = 1.0 / (beta + (v * num) / den);
+    return true;
+}
+
+#if defined(__CUDACC__)
+// 32-lane butterfly of the tree-sum spec; lane 0 holds the group value
+SABC_D double warp_tree(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+}
+// one 256-group: called by all 256 threads of a CTA; result valid in thread 0
+SABC_D double group256(double v, double* s_w /* 8 doubles */) {
+    const double w = warp_tree(v);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = w;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0) { tot = s_w[0]; for (int k = 1; k < 8; ++k) tot = tot + s_w[k]; }
+    __syncthreads();
+    return tot;
+}
+// radix-256 tree sum of x[0..n) by ONE CTA of 256 threads; scratch needs ceil(n/256) doubles.
+// Result valid in thread 0.
+SABC_D double cta_treesum(const double* x, int64_t n, double* scratch, double* s_w) {
+    if (n <= 0) return 0.0;
+    const double* in = x;
+    double* out = scratch;
+    for (;;) {
+        const int64_t g = (n + CHUNK - 1) / CHUNK;
+        double last = 0.0;
+        for (int64_t c = 0; c < g; ++c) {
+            const int64_t i = c * CHUNK + threadIdx.x;
+            const double r = group256(i < n ? in[i] : 0.0, s_w);
+            if (threadIdx.x == 0) { if (g > 1) out[c] = r; last = r; }
+        }
+        if (g == 1) return last;
+        __syncthreads();
+        // ping-pong inside scratch: next level reads what was just written
+        in = out; out = out + g; n = g;
+    }
+}
+// warp sum of 31-bit limbs into 64 bits via two 16-bit hardware reductions
+SABC_D unsigned long long warp_sum_u32(uint32_t x) {
+    const uint32_t lo = __reduce_add_sync(0xffffffffu, x & 0xffffu);
+    const uint32_t hi = __reduce_add_sync(0xffffffffu, x >> 16);
+    return ((unsigned long long)hi << 16) + lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------------
+struct PopView {                 // structure-of-arrays particle state of one GPU (FP64, leading dim ld)
+    double* theta;               // [D][ld]
+    double* u;                   // [S][ld]
+    double* rho;                 // [S][ld]
+    double* lp;                  // [ld] cached logpdf(prior, θ_i)   (reference recomputes it, :318)
+    int64_t ld;
+};
+
+struct UpdateArgs {
+    PopView pop;
+    int64_t act_off, act_n, ina_off, ina_n;   // active / inactive half (local indices)
+    uint32_t particle_base;                   // global index of local particle 0 (Philox counter)
+    int32_t half;
+    uint64_t seed;
+    DevState* ds;
+    const EcdfStat* ecdf;                     // [S] descriptors in HBM
+    double* rho_part;                         // [S][part_ld] per-group ρ sums of this half
+    int64_t part_ld;
+    int32_t n_eps;
+    int32_t top_doubles;                      // staged ECDF index size (doubles)
+    double prop0, prop1;                      // DE: γ0, σ_γ | Stretch: a | RW: β
+    PriorSpec prior;
+    ModelPar mp;
+};
+
+struct InitArgs {
+    PopView pop;
+    int64_t n;
+    uint32_t particle_base;
+    uint64_t seed;
+    DevState* ds;
+    double* rho_part;                         // [S][part_ld] per-group ρ sums
+    int64_t part_ld;
+    PriorSpec prior;
+    ModelPar mp;
+};
+
+template <int D>
+struct InactiveGather {
+    const double* base; int64_t ld;
+    SABC_D double operator()(int c, int64_t i) const { return base[c * ld + i]; }
+};
+
+SABC_D void stage_ecdf_top(const EcdfStat* ecdf, int S, double* s_top) {
+    for (int j = 0; j < S; ++j) {
+        const EcdfStat& e = ecdf[j];
+        const int top = e.nlev - 1;
+        const double* src = e.lev[top];
+        double* dst = s_top + e.top_off;
+        for (int64_t i = threadIdx.x; i < e.cnt[top]; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 update_half: propose -> prior -> simulate+distance -> ECDF -> Metropolis accept, fused with
+// the partial reductions the ε update, the resampling weights and the history need.
+// ------------------------------------------------------------------------------------------------
+template <class M, int PROP>
+__global__ void __launch_bounds__(CHUNK) update_half_kernel(const UpdateArgs a) {
+    constexpr int D = M::D, S = M::S;
+    extern __shared__ double s_top[];
+    __shared__ unsigned long long s_acc[2 * S + 1];
+    __shared__ double s_w[S][8];
+    __shared__ double s_chol[PROP == PROP_RW ? D * D : 1];
+
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 2 * S + 1; k += CHUNK) s_acc[k] = 0ull;
+    if (PROP == PROP_RW) for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k];
+    stage_ecdf_top(a.ecdf, S, s_top);
+
+    const uint64_t sweep = 2ull * (uint64_t)a.ds->t + (uint64_t)a.half;
+    double eps[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) eps[j] = a.ds->eps[a.n_eps == 1 ? 0 : j];
+
+    const int64_t ld = a.pop.ld;
+    const int64_t n_groups = (a.act_n + CHUNK - 1) / CHUNK;
+    const InactiveGather<D> P{a.pop.theta + a.ina_off, ld};
+
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int64_t il = grp * CHUNK + tid;
+        const bool valid = il < a.act_n;
+        const int64_t gi = a.act_off + il;
+        double rp[S], up[S];
+        bool acc = false;
+        if (valid) {
+            const uint32_t pid = a.particle_base + (uint32_t)gi;
+            double th[D], thp[D], lf;
+#pragma unroll
+            for (int c = 0; c < D; ++c) th[c] = a.pop.theta[c * ld + gi];
+            const CtrlWords cw = ctrl_words(a.seed, pid, sweep);
+            if (PROP == PROP_DE) propose_de<D>(th, P, a.ina_n, a.prop0, a.prop1, cw, thp, lf);
+            else if (PROP == PROP_STRETCH) propose_stretch<D>(th, P, a.ina_n, a.prop0, cw, thp, lf);
+            else propose_rw<D>(th, s_chol, a.seed, pid, sweep, thp, lf);
+            const double lpp = prior_logpdf<D>(a.prior, thp);
+            if (lpp > -dinf()) {                                       // :314 (no simulation outside the support)
+                Stream st(a.seed, pid, sweep, KIND_MODEL);
+                M::sim(thp, a.mp, st, rp);                              // :315
+                double Ssum = 0.0;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    up[j] = ecdf_eval(a.ecdf[j], s_top, rp[j]);         // :316
+                    const double t = (a.pop.u[j * ld + gi] - up[j]) / eps[j];
+                    Ssum = (j == 0) ? t : Ssum + t;
+                }
+                const double Lacc = ((lpp - a.pop.lp[gi]) + Ssum) + lf; // :318-319
+                acc = det_log(u53(cw.D)) < Lacc;                        // :324
+            }
+            if (acc) {                                                  // :325-328
+#pragma unroll
+                for (int c = 0; c < D; ++c) a.pop.theta[c * ld + gi] = thp[c];
+#pragma unroll
+                for (int j = 0; j < S; ++j) { a.pop.u[j * ld + gi] = up[j]; a.pop.rho[j * ld + gi] = rp[j]; }
+                a.pop.lp[gi] = lpp;
+            } else {
+#pragma unroll
+                for (int j = 0; j < S; ++j) { up[j] = a.pop.u[j * ld + gi]; rp[j] = a.pop.rho[j * ld + gi]; }
+            }
+        }
+        // epilogue: exact Σu limbs, accept count, per-group ρ tree sums
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            uint32_t hi = 0, lo = 0;
+            if (valid) u_limbs(up[j], hi, lo);
+            const unsigned long long sh = warp_sum_u32(hi), sl = warp_sum_u32(lo);
+            if ((tid & 31) == 0) { atomicAdd(&s_acc[2 * j], sh); atomicAdd(&s_acc[2 * j + 1], sl); }
+            const double w = warp_tree(valid ? rp[j] : 0.0);
+            if ((tid & 31) == 0) s_w[j][tid >> 5] = w;
+        }
+        const uint32_t na = __reduce_add_sync(0xffffffffu, acc ? 1u : 0u);
+        if ((tid & 31) == 0 && na) atomicAdd(&s_acc[2 * S], (unsigned long long)na);
+        __syncthreads();
+        if (tid < S) {
+            double tot = s_w[tid][0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) tot = tot + s_w[tid][k];
+            a.rho_part[tid * a.part_ld + grp] = tot;
+        }
+        __syncthreads();
+    }
+    if (tid < S) { atomicAdd(&a.ds->u_hi[tid], s_acc[2 * tid]); atomicAdd(&a.ds->u_lo[tid], s_acc[2 * tid + 1]); }
+    if (tid == 0 && s_acc[2 * S]) atomicAdd(&a.ds->n_acc_iter, s_acc[2 * S]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 init_prior_sim: θ ~ prior, ρ = f_dist(θ)  (src/SimulatedAnnealingABC.jl:172-179), negative
+// distance check (:185) and per-group ρ sums for ρ_history[1] (:180).
+// ------------------------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(CHUNK) init_prior_sim_kernel(const InitArgs a) {
+    constexpr int D = M::D, S = M::S;
+    __shared__ double s_w[S][8];
+    const int tid = threadIdx.x;
+    const int64_t ld = a.pop.ld;
+    const int64_t n_groups = (a.n + CHUNK - 1) / CHUNK;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int64_t i = grp * CHUNK + tid;
+        const bool valid = i < a.n;
+        double rho[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) rho[j] = 0.0;
+        if (valid) {
+            const uint32_t pid = a.particle_base + (uint32_t)i;
+            double th[D];
+            prior_rand<D>(a.prior, a.seed, pid, th);
+            Stream st(a.seed, pid, 0, KIND_MODEL);
+            M::sim(th, a.mp, st, rho);
+            bool neg = false;
+#pragma unroll
+            for (int c = 0; c < D; ++c) a.pop.theta[c * ld + i] = th[c];
+#pragma unroll
+            for (int j = 0; j < S; ++j) { a.pop.rho[j * ld + i] = rho[j]; neg |= rho[j] < 0.0; }
+            a.pop.lp[i] = prior_logpdf<D>(a.prior, th);
+            if (neg) atomicOr(&a.ds->error_flag, 1);
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const double w = warp_tree(rho[j]);
+            if ((tid & 31) == 0) s_w[j][tid >> 5] = w;
+        }
+        __syncthreads();
+        if (tid < S) {
+            double tot = s_w[tid][0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) tot = tot + s_w[tid][k];
+            a.rho_part[tid * a.part_ld + grp] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Model plug-in registry: one launcher table per model (the template instantiations above).
+// ------------------------------------------------------------------------------------------------
+struct ModelVTable {
+    const char* name;
+    int32_t n_para, n_stats;
+    cudaError_t (*launch_init)(const InitArgs&, int grid, cudaStream_t);
+    cudaError_t (*launch_update)(int proposal, const UpdateArgs&, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*update_occupancy)(int proposal, size_t smem, int* blocks_per_sm);
+    cudaError_t (*simulate)(const double* d_theta, int64_t n, int64_t ld, const ModelPar&, uint64_t seed,
+                            uint32_t particle_base, uint64_t sweep, double* d_rho, cudaStream_t);
+};
+
+template <class M>
+__global__ void simulate_kernel(const double* theta, int64_t n, int64_t ld, const ModelPar mp, uint64_t seed,
+                                uint32_t particle_base, uint64_t sweep, double* rho) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double th[M::D], r[M::S];
+    for (int c = 0; c < M::D; ++c) th[c] = theta[c * ld + i];
+    Stream st(seed, particle_base + (uint32_t)i, sweep, KIND_MODEL);
+    M::sim(th, mp, st, r);
+    for (int j = 0; j < M::S; ++j) rho[j * ld + i] = r[j];
+}
+
+template <class M>
+struct ModelLaunchers {
+    static cudaError_t init(const InitArgs& a, int grid, cudaStream_t s) {
+        init_prior_sim_kernel<M><<<grid, CHUNK, 0, s>>>(a);
+        return cudaGetLastError();
+    }
+    template <int PROP>
+    static cudaError_t upd(const UpdateArgs& a, int grid, size_t smem, cudaStream_t s) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(update_half_kernel<M, PROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        update_half_kernel<M, PROP><<<grid, CHUNK, smem, s>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t update(int proposal, const UpdateArgs& a, int grid, size_t smem, cudaStream_t s) {
+        switch (proposal) {
+            case PROP_DE: return upd<PROP_DE>(a, grid, smem, s);
+            case PROP_STRETCH: return upd<PROP_STRETCH>(a, grid, smem, s);
+            case PROP_RW: return upd<PROP_RW>(a, grid, smem, s);
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    static cudaError_t occupancy(int proposal, size_t smem, int* b) {
+        switch (proposal) {
+            case PROP_DE: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, update_half_kernel<M, PROP_DE>, CHUNK, smem);
+            case PROP_STRETCH: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, update_half_kernel<M, PROP_STRETCH>, CHUNK, smem);
+            case PROP_RW: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, update_half_kernel<M, PROP_RW>, CHUNK, smem);
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    static cudaError_t simulate(const double* th, int64_t n, int64_t ld, const ModelPar& mp, uint64_t seed,
+                                uint32_t pb, uint64_t sweep, double* rho, cudaStream_t s) {
+        simulate_kernel<M><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(th, n, ld, mp, seed, pb, sweep, rho);
+        return cudaGetLastError();
+    }
+    static ModelVTable vtable(const char* name) {
+        return ModelVTable{name, M::D, M::S, &init, &update, &occupancy, &simulate};
+    }
+};
+#endif  // __CUDACC__
+
+}  // namespace sabc

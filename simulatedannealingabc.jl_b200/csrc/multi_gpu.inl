@@ -1,0 +1,174 @@
+// multi_gpu.inl -- one process per GPU, contiguous particle slices.  Included by engine.cu.
+//
+// Per population update only the tiny reductions cross NVLink: one integer all-reduce of the exact
+// Σu limbs + accept count and one FP64 all-reduce of the ρ sums; every rank then solves ε
+// redundantly.  DE/Stretch partners come from the rank's own inactive half.  Resampling is the exact
+// global multinomial of the reference (:129): all ranks draw the same N global variates, each keeps
+// the draws that land in its weight range and ships only the surplus to the ranks that own the
+// destination slots (grouped ncclSend/ncclRecv).
+
+static __global__ void __launch_bounds__(CHUNK) k_mg_mark(int64_t n_global, unsigned long long w_total, unsigned long long my_off,
+                                                   unsigned long long my_w, const unsigned long long* P, int64_t n_local,
+                                                   uint64_t seed, uint32_t rc, unsigned long long* F, int64_t* src) {
+    for (int64_t k = (int64_t)blockIdx.x * CHUNK + threadIdx.x; k < n_global; k += (int64_t)gridDim.x * CHUNK) {
+        const U64x2 w = philox4x32_10((uint32_t)k, rc, (uint32_t)((uint64_t)k >> 32), KIND_RESAMPLE, (uint32_t)seed,
+                                      (uint32_t)(seed >> 32));
+        const unsigned long long r = mulhi64(w.a, w_total);
+        const bool mine = r >= my_off && r - my_off < my_w;
+        int64_t s = -1;
+        if (mine) { s = upper_bound_u64(P, n_local, r - my_off); if (s >= n_local) s = n_local - 1; }
+        F[k] = mine ? 1ull : 0ull;
+        src[k] = s;
+    }
+}
+// pack the selected particles field-major into the send buffer, in draw order
+static __global__ void __launch_bounds__(CHUNK) k_mg_pack(PopView pop, int D, int S, int64_t n_global, const unsigned long long* Fincl,
+                                                   const int64_t* src, double* sb, int64_t sb_ld) {
+    for (int64_t k = (int64_t)blockIdx.x * CHUNK + threadIdx.x; k < n_global; k += (int64_t)gridDim.x * CHUNK) {
+        const int64_t s = src[k];
+        if (s < 0) continue;
+        const int64_t pos = (int64_t)Fincl[k] - 1;
+        for (int c = 0; c < D; ++c) sb[c * sb_ld + pos] = pop.theta[c * pop.ld + s];
+        for (int j = 0; j < S; ++j) sb[(D + j) * sb_ld + pos] = pop.u[j * pop.ld + s];
+        sb[(D + S) * sb_ld + pos] = pop.lp[s];
+    }
+}
+
+static int mg_allreduce_f64(sabc_engine* e, double* d, int n) {
+    SABC_NCCL(nccl_api()->AllReduce(d, d, (size_t)n, ncclFloat64, ncclSum, e->comm.comm, e->stream));
+    return 0;
+}
+static int mg_allreduce_u64(sabc_engine* e, unsigned long long* d, int n) {
+    SABC_NCCL(nccl_api()->AllReduce(d, d, (size_t)n, ncclUint64, ncclSum, e->comm.comm, e->stream));
+    return 0;
+}
+static int mg_allgather_f64(sabc_engine* e, const double* src, double* dst, int64_t n_each) {
+    SABC_NCCL(nccl_api()->AllGather(src, dst, (size_t)n_each, ncclFloat64, e->comm.comm, e->stream));
+    return 0;
+}
+static int mg_allgather_u64_host(sabc_engine* e, const unsigned long long* d_one, unsigned long long* h_all) {
+    MgScratch& s = e->mg;
+    SABC_CUDA(s.wall.ensure((size_t)e->world));
+    SABC_NCCL(nccl_api()->AllGather(d_one, s.wall.p, 1, ncclUint64, e->comm.comm, e->stream));
+    SABC_CUDA(cudaMemcpyAsync(h_all, s.wall.p, sizeof(unsigned long long) * e->world, cudaMemcpyDeviceToHost, e->stream));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+static int mg_any_flag(sabc_engine* e, int* host_flag) {
+    MgScratch& s = e->mg;
+    SABC_CUDA(s.flag.ensure(1));
+    SABC_CUDA(cudaMemcpyAsync(s.flag.p, host_flag, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    SABC_NCCL(nccl_api()->AllReduce(s.flag.p, s.flag.p, 1, ncclInt32, ncclMax, e->comm.comm, e->stream));
+    SABC_CUDA(cudaMemcpyAsync(host_flag, s.flag.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+// Σu limbs + accept count of the running iteration: one integer all-reduce (exact, order-free)
+static int mg_reduce_iteration_sums(sabc_engine* e) {
+    return mg_allreduce_u64(e, &e->b_ds.p->u_hi[0], 2 * MAX_S + 1);
+}
+
+static int launch_update_proposal_mg(sabc_engine* e) {
+    if (e->proposal != PROP_RW) return 0;
+    const int64_t n = e->n_local, groups = (n + CHUNK - 1) / CHUNK;
+    const int grid = (int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8);
+    const int npair = e->D * (e->D + 1) / 2;
+    DevState* ds = e->b_ds.p;
+    k_group_sums<<<grid, CHUNK, 0, e->stream>>>(e->pop.theta, e->pop.ld, n, e->D, e->b_rw_part.p, e->part_ld * 2);
+    k_treesum_cols<<<e->D, CHUNK, 0, e->stream>>>(e->b_rw_part.p, e->part_ld * 2, groups, e->b_scratch.p, e->scratch_ld, e->b_rw_sums.p);
+    SABC_TRY(mg_allreduce_f64(e, e->b_rw_sums.p, e->D));
+    k_rw_means<<<1, 32, 0, e->stream>>>(ds, e->b_rw_sums.p, e->D, e->N);
+    k_rw_cross_sums<<<grid, CHUNK, 0, e->stream>>>(e->pop.theta, e->pop.ld, n, e->D, ds, e->b_rw_part.p, e->part_ld * 2);
+    k_treesum_cols<<<npair, CHUNK, 0, e->stream>>>(e->b_rw_part.p, e->part_ld * 2, groups, e->b_scratch.p, e->scratch_ld, e->b_rw_sums.p);
+    SABC_TRY(mg_allreduce_f64(e, e->b_rw_sums.p, npair));
+    k_rw_chol<<<1, 32, 0, e->stream>>>(ds, e->b_rw_sums.p, e->D, e->N, e->prop_par[0]);
+    SABC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// exact global multinomial resampling over all ranks (resample_population, :124-137)
+static int mg_resample(sabc_engine* e) {
+    MgScratch& s = e->mg;
+    NcclApi* nc = nccl_api();
+    const int G = e->world, me = e->rank;
+    const int64_t n = e->n_local, N = e->N;
+    DevState* ds = e->b_ds.p;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int g_tiles = (int)std::min<int64_t>(n_tiles, (int64_t)e->n_sm * 8);
+    // local weights and prefix sums
+    k_weights<<<g_tiles, CHUNK, 0, e->stream>>>(e->pop, n, e->S, e->delta, ds, e->b_q.p, e->b_tile_sum.p, 1);
+    k_scan_tiles<<<1, 1024, 0, e->stream>>>(e->b_tile_sum.p, n_tiles, e->b_tile_off.p, &ds->w_total, ds, 1);
+    k_prefix<<<g_tiles, CHUNK, 0, e->stream>>>(e->b_q.p, n, e->b_tile_off.p, ds, 1);
+    SABC_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> w(G), cnt(G);
+    SABC_TRY(mg_allgather_u64_host(e, &ds->w_total, w.data()));
+    unsigned long long W = 0, my_off = 0;
+    for (int g = 0; g < G; ++g) { if (g == me) my_off = W; W += w[g]; }
+    if (W == 0) return set_error(SABC_ERR_INVALID, "all resampling weights are zero");
+    // every rank walks the same N global draws and keeps its own
+    SABC_CUDA(s.F.ensure((size_t)N)); SABC_CUDA(s.src.ensure((size_t)N));
+    const int64_t N_tiles = (N + TILE - 1) / TILE;
+    SABC_CUDA(s.tsum.ensure((size_t)N_tiles)); SABC_CUDA(s.toff.ensure((size_t)N_tiles)); SABC_CUDA(s.scalar.ensure(1));
+    const int g_all = (int)std::min<int64_t>((N + CHUNK - 1) / CHUNK, (int64_t)e->n_sm * 8);
+    const int g_alltiles = (int)std::min<int64_t>(N_tiles, (int64_t)e->n_sm * 8);
+    k_mg_mark<<<g_all, CHUNK, 0, e->stream>>>(N, W, my_off, w[me], e->b_q.p, n, e->seed, (uint32_t)e->n_resampling, s.F.p, s.src.p);
+    k_tile_sums<<<g_alltiles, CHUNK, 0, e->stream>>>(s.F.p, N, s.tsum.p);
+    k_scan_tiles<<<1, 1024, 0, e->stream>>>(s.tsum.p, N_tiles, s.toff.p, s.scalar.p, ds, 1);
+    k_prefix<<<g_alltiles, CHUNK, 0, e->stream>>>(s.F.p, N, s.toff.p, ds, 1);
+    SABC_CUDA(cudaGetLastError());
+    SABC_TRY(mg_allgather_u64_host(e, s.scalar.p, cnt.data()));
+    const int64_t c_me = (int64_t)cnt[me];
+    const int nf = e->D + e->S + 1;
+    const int64_t sb_ld = std::max<int64_t>(c_me, 1);
+    SABC_CUDA(s.sb.ensure((size_t)nf * sb_ld));
+    k_mg_pack<<<g_all, CHUNK, 0, e->stream>>>(e->pop, e->D, e->S, N, s.F.p, s.src.p, s.sb.p, sb_ld);
+    SABC_CUDA(cudaGetLastError());
+    // exchange: the selected particles of rank g occupy global slots [C_g, C_g + c_g); rank d owns [d n, (d+1) n)
+    std::vector<int64_t> counts(cnt.begin(), cnt.end()), s_off(G), s_cnt(G), r_off(G), r_cnt(G);
+    SABC_TRY(sabc_mg_exchange_plan(counts.data(), G, n, me, s_off.data(), s_cnt.data(), r_off.data(), r_cnt.data()));
+    auto field_dst = [&](int f) -> double* {
+        if (f < e->D) return e->tmp.theta + (int64_t)f * e->tmp.ld;
+        if (f < e->D + e->S) return e->tmp.u + (int64_t)(f - e->D) * e->tmp.ld;
+        return e->tmp.lp;
+    };
+    for (int f = 0; f < nf; ++f)               // slots I fill from my own selection
+        if (s_cnt[me] > 0)
+            SABC_CUDA(cudaMemcpyAsync(field_dst(f) + r_off[me], s.sb.p + (int64_t)f * sb_ld + s_off[me],
+                                      (size_t)s_cnt[me] * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    SABC_NCCL(nc->GroupStart());
+    for (int f = 0; f < nf; ++f) {
+        for (int d = 0; d < G; ++d)
+            if (d != me && s_cnt[d] > 0)
+                SABC_NCCL(nc->Send(s.sb.p + (int64_t)f * sb_ld + s_off[d], (size_t)s_cnt[d], ncclFloat64, d, e->comm.comm, e->stream));
+        for (int g = 0; g < G; ++g)
+            if (g != me && r_cnt[g] > 0)
+                SABC_NCCL(nc->Recv(field_dst(f) + r_off[g], (size_t)r_cnt[g], ncclFloat64, g, e->comm.comm, e->stream));
+    }
+    SABC_NCCL(nc->GroupEnd());
+    const int g_grp = (int)std::min<int64_t>((n + CHUNK - 1) / CHUNK, (int64_t)e->n_sm * 8);
+    k_copyback<<<g_grp, CHUNK, 0, e->stream>>>(e->pop, e->tmp, n, e->D, e->S, ds, 1);
+    k_sum_u<<<g_grp, CHUNK, 0, e->stream>>>(e->pop.u, e->pop.ld, n, e->S, &ds->r_hi[0], &ds->r_lo[0]);
+    SABC_CUDA(cudaGetLastError());
+    SABC_TRY(mg_allreduce_u64(e, &ds->r_hi[0], 2 * MAX_S));
+    e->n_resampling += 1;
+    return 0;
+}
+
+// one population update on this rank's slice
+static int mg_iteration(sabc_engine* e) {
+    DevState* ds = e->b_ds.p;
+    SABC_TRY(launch_update_half(e, 0));
+    SABC_TRY(launch_update_half(e, 1));
+    SABC_TRY(launch_post1(e, 0));
+    SABC_TRY(mg_reduce_iteration_sums(e));
+    SABC_TRY(mg_allreduce_f64(e, &ds->rho_sum[0][0], 2 * MAX_S));
+    k_decide<<<1, 32, 0, e->stream>>>(ds, e->S, e->N, e->resample);
+    SABC_CUDA(cudaGetLastError());
+    int flag = 0;
+    SABC_CUDA(cudaMemcpyAsync(&flag, &ds->resample_flag, sizeof flag, cudaMemcpyDeviceToHost, e->stream));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    if (flag) SABC_TRY(mg_resample(e));
+    SABC_TRY(launch_update_proposal_mg(e));
+    SABC_TRY(launch_finish(e));
+    return 0;
+}

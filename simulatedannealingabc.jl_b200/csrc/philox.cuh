@@ -1,0 +1,113 @@
+// philox.cuh -- counter-based random streams and samplers.
+//
+// The reference draws from Julia's task-local Xoshiro (rand()/randn() inside the @threads loops,
+// src/SimulatedAnnealingABC.jl:172-179,308-331), which is neither reproducible across thread
+// counts nor portable to a GPU.  Here every (particle, sweep, purpose) owns a Philox4x32-10
+// stream addressed by its counter, so a particle update needs no RNG state in HBM and the result
+// does not depend on the launch geometry.
+#pragma once
+#include "detmath.cuh"
+
+namespace sabc {
+
+enum StreamKind : uint32_t { KIND_CTRL = 0, KIND_MODEL = 1, KIND_RW = 3, KIND_PRIOR = 4, KIND_RESAMPLE = 6 };
+
+struct U64x2 { uint64_t a, b; };
+
+SABC_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+SABC_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11)
+SABC_HD U64x2 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    U64x2 o;
+    o.a = (uint64_t)c0 | ((uint64_t)c1 << 32);
+    o.b = (uint64_t)c2 | ((uint64_t)c3 << 32);
+    return o;
+}
+
+// A stream = (seed, particle, sweep, kind); block j of it is one Philox call.
+struct Stream {
+    uint32_t k0, k1, particle, sweep_lo, tag, next;
+    SABC_HD Stream(uint64_t seed, uint32_t particle_, uint64_t sweep, uint32_t kind)
+        : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), particle(particle_), sweep_lo((uint32_t)sweep),
+          tag(kind | ((uint32_t)(sweep >> 32) << 4)), next(0) {}
+    SABC_HD U64x2 block(uint32_t j) const { return philox4x32_10(particle, sweep_lo, j, tag, k0, k1); }
+    SABC_HD U64x2 draw() { return block(next++); }
+};
+
+SABC_HD double u53(uint64_t x) { return (double)(x >> 11) * 0x1p-53; }              // [0,1)
+SABC_HD double u53_open0(uint64_t x) { return (double)((x >> 11) + 1) * 0x1p-53; }  // (0,1]
+
+// Box-Muller pair from one block; stands in for randn()
+SABC_HD void normal_pair(const U64x2 w, double& z0, double& z1) {
+    const double r = sqrt(-2.0 * det_log(u53_open0(w.a)));
+    double sn, cs;
+    det_sincos2pi(u53(w.b), sn, cs);
+    z0 = r * cs; z1 = r * sn;
+}
+// one normal from a single 64-bit word (two 32-bit uniforms) -- the DE gamma jitter
+SABC_HD double normal32(uint64_t c) {
+    const double u1 = (double)((c & 0xffffffffULL) + 1) * 0x1p-32;
+    const double u2 = (double)(c >> 32) * 0x1p-32;
+    return sqrt(-2.0 * det_log(u1)) * det_cos2pi(u2);
+}
+
+// Poisson(lam): one-uniform sequential-search inversion below 10, Hoermann's PTRS (1993) above.
+// The slow-path logarithms are evaluated lazily; the value drawn does not depend on that.
+SABC_HD int64_t poisson(double lam, Stream& st) {
+    if (!(lam > 0.0)) return 0;
+    if (lam < 10.0) {
+        const double U = u53(st.draw().a);
+        double p = det_exp(-lam), F = p;
+        int64_t k = 0;
+        while (U > F && k < 1024) { k++; p = (p * lam) / (double)k; F = F + p; }
+        return k;
+    }
+    const double slam = sqrt(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        const U64x2 w = st.draw();
+        const double U = u53(w.a) - 0.5, V = u53(w.b);
+        const double us = 0.5 - fabs(U);
+        const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) return (int64_t)kf;
+        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+        const double loglam = det_log(lam);
+        const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+        const double lhs = det_log(V) + det_log(invalpha) - det_log(a / (us * us) + b);
+        const double rhs = (-lam + kf * loglam) - det_logfact(kf);
+        if (lhs <= rhs) return (int64_t)kf;
+    }
+}
+
+// exact, order-independent accumulation of u in [0,1]: u*2^62 split into two 31-bit limbs (§3.4)
+SABC_HD void u_limbs(double u, uint32_t& hi, uint32_t& lo) {
+    double c = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+    if (c != c) c = 0.0;
+    const uint64_t q = (uint64_t)(c * 0x1p62);
+    hi = (uint32_t)(q >> 31); lo = (uint32_t)(q & 0x7fffffffULL);
+}
+SABC_HD double limbs_to_sum(uint64_t hi, uint64_t lo) { return ((double)hi * 2147483648.0 + (double)lo) * 0x1p-62; }
+
+}  // namespace sabc

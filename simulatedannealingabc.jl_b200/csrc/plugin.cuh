@@ -1,0 +1,270 @@
+// plugin.cuh -- operator plug-ins of the SABC hot path: prior, proposals, ECDF lookup, models.
+//
+// These are the device forms of the reference's plug points:
+//   prior     : rand(prior) / logpdf(prior, θ)      src/SimulatedAnnealingABC.jl:163,174,314,318
+//   proposal  : (p::Proposal)(θ, population_inactive)  src/proposals.jl:40-55,101-114,137-148
+//   G (ECDF)  : cdfs_dist_prior(ρ)                  src/cdf_estimators.jl:68-70
+//   f_dist    : user model + distance               src/SimulatedAnnealingABC.jl:315,421
+// Everything is header-only so that a model plug-in compiled out of tree instantiates the same
+// fused kernels (kernels.cuh) and registers its launchers (sabc_register_model).
+#pragma once
+#include "philox.cuh"
+
+namespace sabc {
+
+constexpr int MAX_D = 8;            // max parameters per particle
+constexpr int MAX_S = 32;           // max summary statistics
+constexpr int MAX_MODEL_PAR = 40;   // doubles in a model parameter blob
+constexpr int ECDF_MAX_LEVELS = 8;
+constexpr int ECDF_FANOUT = 16;     // one 128-byte line of knots per index node
+constexpr int CHUNK = 256;          // particles per tree-sum group == threads per CTA
+
+enum Algorithm : int32_t { ALG_SINGLE_EPS = 0, ALG_MULTI_EPS = 1 };
+enum ProposalKind : int32_t { PROP_DE = 0, PROP_STRETCH = 1, PROP_RW = 2 };
+enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// Prior: product of independent univariates (Distributions ^0.25 formulas)
+// ------------------------------------------------------------------------------------------------
+struct PriorSpec {
+    int32_t n;
+    int32_t kind[MAX_D];
+    double p0[MAX_D], p1[MAX_D];   // Uniform(a,b) | Normal(mu,sigma)
+    double c[MAX_D];               // -log(b-a)    | log(sigma)   (det_log, filled by prior_prepare)
+};
+
+inline void prior_prepare(PriorSpec& p) {
+    for (int i = 0; i < p.n; ++i)
+        p.c[i] = p.kind[i] == PRIOR_NORMAL ? det_log(p.p1[i]) : -det_log(p.p1[i] - p.p0[i]);
+}
+
+template <int D>
+SABC_HD double prior_logpdf(const PriorSpec& p, const double (&th)[D]) {
+    double lp = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        double t;
+        if (p.kind[c] == PRIOR_NORMAL) {
+            const double z = (th[c] - p.p0[c]) / p.p1[c];
+            t = -((z * z + 0x1.d67f1c864beb5p+0) * 0.5) - p.c[c];
+        } else {
+            t = (th[c] >= p.p0[c] && th[c] <= p.p1[c]) ? p.c[c] : -dinf();
+        }
+        lp = (c == 0) ? t : lp + t;
+    }
+    return lp;
+}
+
+template <int D>
+SABC_HD void prior_rand(const PriorSpec& p, uint64_t seed, uint32_t particle, double (&th)[D]) {
+    const Stream st(seed, particle, 0, KIND_PRIOR);
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const U64x2 w = st.block((uint32_t)c);
+        if (p.kind[c] == PRIOR_NORMAL) {
+            double z0, z1; normal_pair(w, z0, z1);
+            th[c] = p.p0[c] + p.p1[c] * z0;
+        } else {
+            th[c] = p.p0[c] + (p.p1[c] - p.p0[c]) * u53(w.a);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Proposals.  P(c, i) reads coordinate c of particle i of the inactive half.
+// ------------------------------------------------------------------------------------------------
+struct CtrlWords { uint64_t A, B, C, D; };   // blocks 0 and 1 of the control stream
+
+SABC_HD CtrlWords ctrl_words(uint64_t seed, uint32_t particle, uint64_t sweep) {
+    const Stream st(seed, particle, sweep, KIND_CTRL);
+    const U64x2 b0 = st.block(0), b1 = st.block(1);
+    return CtrlWords{b0.a, b0.b, b1.a, b1.b};
+}
+
+template <int D, class Gather>
+SABC_HD void propose_de(const double (&th)[D], const Gather& P, int64_t M, double gamma0, double sigma_gamma,
+                        const CtrlWords& cw, double (&out)[D], double& log_factor) {
+    int64_t i1 = (int64_t)mulhi64(cw.A, (uint64_t)M);               // proposals.jl:103-107
+    int64_t i2 = (int64_t)mulhi64(cw.B, (uint64_t)(M - 1));
+    if (i2 >= i1) i2++;
+    const double g = gamma0 * (1.0 + sigma_gamma * normal32(cw.C)); // :110
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[c] = th[c] + g * (P(c, i1) - P(c, i2));   // :113
+    log_factor = 0.0;
+}
+
+template <int D, class Gather>
+SABC_HD void propose_stretch(const double (&th)[D], const Gather& P, int64_t M, double a, const CtrlWords& cw,
+                             double (&out)[D], double& log_factor) {
+    const int64_t i = (int64_t)mulhi64(cw.A, (uint64_t)M);          // proposals.jl:141
+    const double t = (a - 1.0) * u53(cw.B) + 1.0;
+    const double z = (t * t) / a;                                   // :144
+    log_factor = det_log(z) * (double)(D - 1);                      // :146
+#pragma unroll
+    for (int c = 0; c < D; ++c) { const double p = P(c, i); out[c] = p + z * (th[c] - p); }   // :147
+}
+
+// chol: row-major lower Cholesky factor of Σ (D>1) or sqrt(Σ) (D==1)   proposals.jl:42,54
+template <int D>
+SABC_HD void propose_rw(const double (&th)[D], const double* chol, uint64_t seed, uint32_t particle, uint64_t sweep,
+                        double (&out)[D], double& log_factor) {
+    Stream st(seed, particle, sweep, KIND_RW);
+    double z[D + 1];
+#pragma unroll
+    for (int c = 0; c < D; c += 2) normal_pair(st.draw(), z[c], z[c + 1 < D ? c + 1 : D]);
+    if (D == 1) {
+        out[0] = th[0] + chol[0] * z[0];
+    } else {
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c <= r; ++c) { const double t = chol[r * D + c] * z[c]; acc = (c == 0) ? t : acc + t; }
+            out[r] = th[r] + acc;
+        }
+    }
+    log_factor = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ECDF: sorted knots K[0..L) in HBM plus a 16-ary sampled index (level k+1 = every 16th entry of
+// level k); the top level is staged in shared memory.  Evaluation follows Interpolations.jl's
+// LinearMonotonicInterpolation + Flat() exactly: bracket by
+// searchsortedfirst-1, slope by division, one rounded multiply then one rounded add.
+// ------------------------------------------------------------------------------------------------
+struct EcdfStat {
+    const double* lev[ECDF_MAX_LEVELS];   // lev[0] = knots
+    int64_t cnt[ECDF_MAX_LEVELS];
+    int64_t L;
+    double kmax;                          // K[L-1]
+    int32_t nlev;                         // levels incl. knots; lev[nlev-1] is the staged one
+    int32_t top_off;                      // offset (doubles) of the staged level in shared memory
+};
+
+// number of entries of sorted a[0..n) that are < x
+SABC_HD int64_t count_less(const double* a, int64_t n, double x) {
+    int64_t lo = 0;
+    while (n > 0) {
+        const int64_t half = n >> 1;
+        if (a[lo + half] < x) { lo += half + 1; n -= half + 1; } else { n = half; }
+    }
+    return lo;
+}
+
+SABC_D double ecdf_eval(const EcdfStat& e, const double* s_top, double rho) {
+    const double x = rho > e.kmax ? e.kmax : (rho < 0.0 ? 0.0 : rho);        // Flat(): clamp to [K_1, K_L]
+    const int top = e.nlev - 1;
+    int64_t lb = count_less(s_top + e.top_off, e.cnt[top], x);              // searchsortedfirst on the top level
+    for (int lv = top - 1; lv >= 0; --lv) {
+        if (lb > 0) {
+            const int64_t base = (lb - 1) * ECDF_FANOUT;
+            int64_t n = e.cnt[lv] - base; if (n > ECDF_FANOUT) n = ECDF_FANOUT;
+            lb = base + count_less(e.lev[lv] + base, n, x);
+        }
+    }
+    int64_t j = lb > 0 ? lb - 1 : 0;                                          // k > 1 && (k -= 1)
+    if (j > e.L - 2) j = e.L - 2;
+    const double* K = (top == 0) ? (s_top + e.top_off) : e.lev[0];
+    const double kj = K[j], kj1 = K[j + 1];
+    const double Lm1 = (double)(e.L - 1);
+    const double y0 = (double)j / Lm1, y1 = (double)(j + 1) / Lm1;           // range(0, stop=1, length=L)
+    const double m = (y1 - y0) / (kj1 - kj);
+    return y0 + m * (x - kj);
+}
+
+// host/CPU-free reference form used by the unit hook kernel (plain binary search over the knots)
+SABC_HD double ecdf_eval_flat(const double* K, int64_t L, double rho) {
+    const double x = rho > K[L - 1] ? K[L - 1] : (rho < K[0] ? K[0] : rho);
+    int64_t j = count_less(K, L, x);
+    if (j > 0) j -= 1;
+    if (j > L - 2) j = L - 2;
+    const double Lm1 = (double)(L - 1);
+    const double y0 = (double)j / Lm1, y1 = (double)(j + 1) / Lm1;
+    const double m = (y1 - y0) / (K[j + 1] - K[j]);
+    return y0 + m * (x - K[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Models (device f_dist).  A model is a struct with
+//   static constexpr int D, S;                         parameters, statistics
+//   static __device__ void sim(th, par, stream, rho)   simulate + distance(s) >= 0
+// ------------------------------------------------------------------------------------------------
+struct ModelPar { double v[MAX_MODEL_PAR]; };
+
+// C1/C5: 1-D Gaussian mean, sufficient-statistic form.  par: ybar_obs, sd_mean (= sigma/sqrt(n))
+struct GaussMean {
+    static constexpr int D = 1, S = 1;
+    SABC_HD static void sim(const double (&th)[1], const ModelPar& mp, Stream& st, double (&rho)[1]) {
+        double z0, z1; normal_pair(st.draw(), z0, z1);
+        const double ysim = th[0] + mp.v[1] * z0;
+        rho[0] = fabs(ysim - mp.v[0]);
+    }
+};
+
+// n iid draws N(θ1, θ2 or fixed σ); statistics |obs1 - mean|, |obs2 - mean(y²) or Σy²|
+// (test/runtests.jl:35,86,128-131,167-170; docs/src/usage.md:16-35).  par: n, sigma_fixed, obs1, obs2, stat2_kind
+template <int D_, int S_>
+struct GaussSample {
+    static constexpr int D = D_, S = S_;
+    SABC_HD static void sim(const double (&th)[D_], const ModelPar& mp, Stream& st, double (&rho)[S_]) {
+        const int n = (int)mp.v[0];
+        const double sig = D_ >= 2 ? th[D_ - 1] : mp.v[1];
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < n; k += 2) {
+            double z0, z1; normal_pair(st.draw(), z0, z1);
+            double y = th[0] + sig * z0;
+            s1 = s1 + y; s2 = s2 + y * y;
+            if (k + 1 < n) { y = th[0] + sig * z1; s1 = s1 + y; s2 = s2 + y * y; }
+        }
+        rho[0] = fabs(mp.v[2] - s1 / (double)n);
+        if (S_ >= 2) rho[S_ - 1] = fabs(mp.v[3] - (mp.v[4] != 0.0 ? s2 : s2 / (double)n));
+    }
+};
+
+// C3: stochastic logistic growth, θ = (r, K, σ), T = 20 points.  par: x0, T, obs[T]
+struct Logistic {
+    static constexpr int D = 3, S = 20;
+    SABC_HD static void sim(const double (&th)[3], const ModelPar& mp, Stream& st, double (&rho)[20]) {
+        double x = mp.v[0];
+#pragma unroll
+        for (int t = 0; t < S; t += 2) {
+            double z[2]; normal_pair(st.draw(), z[0], z[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double grow = (th[0] * x) * (1.0 - x / th[1]);
+                const double noise = (th[2] * x) * z[h];
+                x = (x + grow) + noise;
+                if (!(x > 0.0)) x = 0.0;
+                rho[t + h] = fabs(x - mp.v[2 + t + h]);
+            }
+        }
+    }
+};
+
+// C4: SIR tau-leap, θ = (β, γ, ι, φ).  par: pop, T, tau, obs_total, obs_peak, obs_tpeak
+struct SirTauLeap {
+    static constexpr int D = 4, S = 3;
+    SABC_HD static void sim(const double (&th)[4], const ModelPar& mp, Stream& st, double (&rho)[3]) {
+        const double pop = mp.v[0], tau = mp.v[2];
+        const int T = (int)mp.v[1];
+        int64_t I = (int64_t)floor(th[2] * pop + 0.5);
+        if (I < 0) I = 0;
+        if (I > (int64_t)pop) I = (int64_t)pop;
+        int64_t Sc = (int64_t)pop - I;
+        int64_t total = 0, peak = -1, tpeak = 0;
+        for (int t = 1; t <= T; ++t) {
+            const double li = (((th[0] * (double)Sc) * (double)I) / pop) * tau;
+            int64_t ninf = poisson(li, st); if (ninf > Sc) ninf = Sc;
+            const double lr = (th[1] * (double)I) * tau;
+            int64_t nrec = poisson(lr, st); if (nrec > I) nrec = I;
+            Sc -= ninf; I += ninf - nrec;
+            const int64_t c = poisson(th[3] * (double)ninf, st);
+            total += c;
+            if (c > peak) { peak = c; tpeak = t; }
+        }
+        const double d0 = (double)total - mp.v[3], d1 = (double)peak - mp.v[4], d2 = (double)tpeak - mp.v[5];
+        rho[0] = d0 * d0; rho[1] = d1 * d1; rho[2] = d2 * d2;
+    }
+};
+
+}  // namespace sabc

@@ -1,0 +1,186 @@
+"""GPU parity of the whole path: initialization() + update_population!() on the device against the oracle on the same
+Philox streams.  DE and Stretch trajectories must be bit-identical (population, u, rho, eps history, counters); north_star
+check (2) asks for eps trajectories within 1e-6 relative -- bit identity is stronger.  RandomWalk goes through FP64 tree sums
+that both sides define identically, so it is bit-identical too."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import sabc_b200 as sb
+from helpers import assert_same_state, make_pair, model_cases
+
+pytestmark = pytest.mark.gpu
+
+DE = lambda d: sb.DifferentialEvolution(n_para=d)   # noqa: E731
+
+
+def run_pair(model, prior, n_particles, n_updates, algorithm="single_eps", proposal=None, resample=None, v=1.0, delta=0.1,
+             checkpoint=1, flags=0, seed=0x5ABC):
+    proposal = proposal or DE(model.n_para)
+    kw = dict(n_particles=n_particles, algorithm=algorithm, proposal=proposal, resample=resample or 2 * n_particles, v=v, delta=delta, seed=seed)
+    eng, orc = make_pair(model, prior, flags=flags, **kw)
+    eng.init(); orc.init()
+    assert_same_state(eng, orc, "after init")
+    for j in range(model.n_stats):
+        assert np.array_equal(eng.get_ecdf(j), orc.get_ecdf(j))
+    eng.update(n_updates * n_particles, checkpoint); orc.update(n_updates * n_particles, checkpoint)
+    assert_same_state(eng, orc, f"after {n_updates} updates")
+    for name, a, b in zip(("eps_h", "u_h", "rho_h"), eng.get_history(), orc.get_history()):
+        assert a.shape == b.shape, (name, a.shape, b.shape)
+        assert np.array_equal(a, b), f"{name}: max rel diff {np.max(np.abs(a - b) / np.abs(b))}"
+    return eng, orc
+
+
+def test_c1_gauss_mean_trajectory(gpu):
+    """BASELINE configs[0]: 1-D Gaussian, N=1000, n_simulation=1e5 (99 population updates)."""
+    model, prior = model_cases()["gauss_mean"]
+    eng, orc = run_pair(model, prior, 1000, 99)
+    eps, cnt = eng.get_state()
+    assert cnt[0] == 100_000 and cnt[3] == 99 and cnt[2] >= 2 and eps[0] < 0.05
+
+
+@pytest.mark.parametrize("name", ["gauss_sample_d1s1", "gauss_sample_d2s1", "gauss_sample_d1s2", "gauss_sample_d2s2", "logistic", "sir_tauleap"])
+@pytest.mark.parametrize("algorithm", ["single_eps", "multi_eps"])
+def test_models_trajectory(gpu, name, algorithm):
+    model, prior = model_cases()[name]
+    run_pair(model, prior, 600, 12, algorithm=algorithm, resample=600)
+
+
+@pytest.mark.parametrize("prop", ["stretch", "rw"])
+@pytest.mark.parametrize("name", ["gauss_mean", "gauss_sample_d2s2", "sir_tauleap"])
+def test_proposals_trajectory(gpu, name, prop):
+    model, prior = model_cases()[name]
+    proposal = sb.StretchMove() if prop == "stretch" else sb.RandomWalk(n_para=model.n_para)
+    run_pair(model, prior, 700, 10, proposal=proposal, resample=700)
+
+
+@pytest.mark.parametrize("n", [4, 5, 255, 257, 513, 2050])
+def test_ragged_sizes(gpu, n):
+    """odd N (halves N÷2 and N−N÷2, :300-301), sizes around the 256-particle group and the 2048 scan tile."""
+    model, prior = model_cases()["gauss_sample_d2s2"]
+    run_pair(model, prior, n, 6, algorithm="multi_eps", resample=max(2, n // 2))
+
+
+def test_larger_population_multilevel_ecdf(gpu):
+    """N = 300k: ECDF table > one index level, several scan tiles, many resamplings."""
+    model, prior = model_cases()["gauss_mean"]
+    eng, orc = run_pair(model, prior, 300_000, 8, resample=100_000)
+    assert eng.get_state()[1][2] >= 3
+
+
+def test_graph_and_direct_launch_agree(gpu):
+    model, prior = model_cases()["gauss_sample_d2s2"]
+    states = []
+    for flags in (0, sb.SABC_FLAG_NO_GRAPH, sb.SABC_FLAG_TIME_KERNELS):
+        eng = sb.Engine(model, prior, n_particles=5000, algorithm="multi_eps", proposal=DE(2), resample=5000, v=1.0, delta=0.1, flags=flags)
+        eng.init(); eng.update(15 * 5000)
+        states.append((eng.get_population(), eng.get_state(), eng.timing()))
+    for (p, s, t) in states[1:]:
+        for a, b in zip(p, states[0][0]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(s[0], states[0][1][0]) and np.array_equal(s[1], states[0][1][1])
+    assert states[2][2]["kernel_ms"] > 0 and states[2][2]["kernel_launches"] == 30
+
+
+def test_checkpoint_history_striding(gpu):
+    """history every k-th update plus a final record (:367-382)."""
+    model, prior = model_cases()["gauss_mean"]
+    eng, orc = run_pair(model, prior, 500, 10, checkpoint=4)
+    e, u, r = eng.get_history()
+    assert e.shape[0] == 1 + 2 + 1      # init, ix=4, ix=8, final
+
+
+def test_resume_matches_single_run(gpu):
+    """update_population! continues an existing result (:251-271,387-397; test/runtests.jl:67-71)."""
+    model, prior = model_cases()["gauss_sample_d1s2"]
+    kw = dict(n_particles=800, algorithm="single_eps", proposal=DE(1), resample=800, v=1.0, delta=0.1)
+    a = sb.Engine(model, prior, **kw); a.init(); a.update(20 * 800)
+    b = sb.Engine(model, prior, **kw); b.init(); b.update(9 * 800); b.update(11 * 800)
+    for x, y in zip(a.get_population(), b.get_population()):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a.get_state()[0], b.get_state()[0]) and np.array_equal(a.get_state()[1], b.get_state()[1])
+    # n_simulation < n_particles: no update at all (test/runtests.jl:75-78)
+    before = b.get_state()[1].copy(); nh = b.get_history()[0].shape[0]
+    b.update(50)
+    assert np.array_equal(b.get_state()[1], before) and b.get_history()[0].shape[0] == nh
+
+
+def test_host_round_trip(gpu):
+    """SABCresult held on the host: upload, update, download (sabc_update_host) equals the device-resident run, and a
+    second engine can be resumed from (theta,u,rho,eps,counters,ECDF knots) alone."""
+    model, prior = model_cases()["gauss_sample_d2s2"]
+    kw = dict(n_particles=1000, algorithm="multi_eps", proposal=DE(2), resample=1000, v=1.0, delta=0.1)
+    a = sb.Engine(model, prior, **kw); a.init(); a.update(5 * 1000)
+    th, u, rho = a.get_population(); eps, cnt = a.get_state()
+    b = sb.Engine(model, prior, **kw)
+    for j in range(2):
+        b.set_ecdf(j, a.get_ecdf(j))
+    th2, u2, rho2, eps2, cnt2 = th.copy(order="F"), u.copy(order="F"), rho.copy(order="F"), eps.copy(), cnt.copy()
+    b.update_host(th2, u2, rho2, eps2, cnt2, 7 * 1000)
+    a.update(7 * 1000)
+    for x, y in zip(a.get_population(), (th2, u2, rho2)):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a.get_state()[0], eps2) and np.array_equal(a.get_state()[1], cnt2)
+    t = b.timing()
+    assert t["h2d_ms"] > 0 and t["d2h_ms"] > 0
+
+
+def test_negative_distance_is_an_error(gpu):
+    """:185 -- a model returning negative prior distances aborts initialization (obs far below gives |.| >= 0, so use the
+    second statistic of gauss_sample with a NaN-free negative trick: obs2 = -inf makes |obs2 - x| = inf, not negative; the
+    device check is exercised through the flag instead)."""
+    model = sb.models.gauss_mean(float("nan"))       # rho = |y - NaN| = NaN: not negative, not positive -> no knots
+    eng = sb.Engine(model, sb.Normal(0, 1), n_particles=100, algorithm="single_eps", proposal=DE(1), resample=200, v=1.0, delta=0.1)
+    with pytest.raises(sb.SABCError) as ei:
+        eng.init()
+    assert ei.value.code == -8                       # build_cdf: maximum() of an empty collection
+
+
+def test_public_api_counters(gpu):
+    """test/runtests.jl:56-78 through the mirrored sabc()/update_population!() surface."""
+    f_dist, prior = model_cases()["gauss_sample_d1s1"]
+    for algorithm in ("multi_eps", "single_eps"):
+        res = sb.sabc(f_dist, prior, n_particles=100, n_simulation=1000, algorithm=algorithm)
+        assert res.state.n_simulation <= 1000 and res.state.n_population_updates == 9 and len(res.population) == 100
+        sb.update_population(res, f_dist, prior, n_simulation=1000)
+        assert res.state.n_simulation <= 2000 and res.state.n_population_updates == 19
+        n_sim = res.state.n_simulation
+        sb.update_population(res, f_dist, prior, n_simulation=50)
+        assert res.state.n_simulation == n_sim
+        assert "Approximate posterior sample with 100 particles" in repr(res)
+    f2, p2 = model_cases()["gauss_sample_d2s2"]
+    for algorithm in ("multi_eps", "single_eps"):
+        res = sb.sabc(f2, p2, n_particles=100, n_simulation=1000, algorithm=algorithm)
+        assert np.all(res.state.eps < 1) and res.population.shape == (100, 2) and res.u.shape == (100, 2)      # :140,179
+    for p in (sb.DifferentialEvolution(n_para=2), sb.StretchMove(), sb.RandomWalk(n_para=2)):                  # :238-266
+        res = sb.sabc(f2, p2, proposal=p, n_particles=100, n_simulation=1000)
+        sb.update_population(res, f2, p2, proposal=p, n_simulation=1000)
+        assert res.state.n_simulation <= 2000
+    with pytest.raises(RuntimeError):
+        sb.update_population(res, f2, p2, n_simulation=1000, v=-0.1)
+    with pytest.raises(RuntimeError):
+        sb.update_population(res, f2, p2, n_simulation=1000, delta=-0.1)
+
+
+def test_posterior_matches_conjugate_and_oracle(gpu):
+    """north_star check (3) on C1: slow annealing (v = 0.02) so the ensemble stays near equilibrium; mean and variance within
+    2 MC standard errors of N(10/11, 1/11) with the MC error estimated from independent runs, and a KS test against the
+    oracle's particles from other seeds."""
+    from scipy import stats
+    model, prior = model_cases()["gauss_mean"]
+    N, n_upd = 4000, 400
+    means, vars_, pops = [], [], []
+    for seed in range(6):
+        eng = sb.Engine(model, prior, n_particles=N, algorithm="single_eps", proposal=DE(1), resample=2 * N, v=0.02, delta=0.1, seed=100 + seed)
+        eng.init(); eng.update(n_upd * N)
+        th = eng.get_population()[0][:, 0]
+        means.append(th.mean()); vars_.append(th.var()); pops.append(th)
+    se_m = np.std(means, ddof=1) / np.sqrt(len(means)); se_v = np.std(vars_, ddof=1) / np.sqrt(len(vars_))
+    assert abs(np.mean(means) - 10 / 11) < 2 * se_m, (np.mean(means), se_m)
+    assert abs(np.mean(vars_) - 1 / 11) < 2 * se_v, (np.mean(vars_), se_v)
+    orc = ob.OracleEngine(model, prior, n_particles=N, algorithm="single_eps", proposal=DE(1), resample=2 * N, v=0.02, delta=0.1, seed=999)
+    orc.init(); orc.update(n_upd * N)
+    tho = orc.get_population()[0][:, 0]
+    # thin to reduce the within-run correlation the KS test ignores
+    p = stats.ks_2samp(pops[0][::8], tho[::8]).pvalue
+    assert p > 0.01, p

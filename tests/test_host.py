@@ -1,0 +1,156 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/sabc_b200.h declares, argument
+validation mirrors the reference's errors, proposals' constructors behave like src/proposals.jl, and compute entry points
+fail loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import sabc_b200 as sb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sabc_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sabc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 40
+    lib = sb._lib.lib()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sabc_b200.h but not exported"
+        assert n in sb._lib.SYMBOLS, f"{n} has no ctypes signature"
+    out = subprocess.run(["nm", "-D", "--defined-only", sb._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (sabc_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    assert lib.sabc_abi_version() == 1
+
+
+def test_cuda_code_is_sm_100a():
+    out = subprocess.run(["cuobjdump", "-lelf", sb._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_model_registry():
+    names = sb.models.registered()
+    for n in ("gauss_mean", "gauss_sample_d1s1", "gauss_sample_d2s2", "logistic", "sir_tauleap"):
+        assert n in names
+    d, s = C.c_int32(), C.c_int32()
+    assert sb._lib.lib().sabc_model_info(b"sir_tauleap", C.byref(d), C.byref(s)) == 0 and (d.value, s.value) == (4, 3)
+    assert sb._lib.lib().sabc_model_info(b"nope", C.byref(d), C.byref(s)) == -20
+
+
+def test_proposal_constructors():
+    """test/runtests.jl:202-209 and src/proposals.jl:29-36,85-99."""
+    with pytest.raises(TypeError):
+        sb.DifferentialEvolution(1, 0.1)            # positional arguments: MethodError in Julia
+    with pytest.raises(TypeError):
+        sb.DifferentialEvolution(1)
+    with pytest.raises(ValueError):
+        sb.DifferentialEvolution(gamma0=1, n_para=5)
+    with pytest.raises(ValueError):
+        sb.DifferentialEvolution(gamma0=1, n_para=5, sigma_gamma=1.4)
+    with pytest.raises(ValueError):
+        sb.DifferentialEvolution()
+    assert sb.DifferentialEvolution(n_para=2).params() == (2.38 / 2.0, 1e-5)
+    assert sb.DifferentialEvolution(**{"γ0": 0.7}).params() == (0.7, 1e-5)
+    assert sb.StretchMove().params() == (2.0, 0.0)
+    assert sb.RandomWalk(n_para=2).params() == (0.8, 0.0)
+    for bad in (0.0, -0.1, 1.1):
+        with pytest.raises(RuntimeError):
+            sb.RandomWalk(n_para=1, beta=bad)
+
+
+def test_argument_validation_before_any_device_work():
+    model, prior = sb.models.gauss_mean(1.0), sb.Normal(0, 1)
+    with pytest.raises(RuntimeError, match="too small"):                  # :155-156; test/runtests.jl:39-54
+        sb.sabc(model, prior, n_particles=100, n_simulation=10)
+    with pytest.raises(RuntimeError, match="too small"):
+        sb.sabc(model, prior, n_particles=100, n_simulation=10, v=-0.1)
+    with pytest.raises(RuntimeError, match="algorithm"):                  # :462-464
+        sb.sabc(model, prior, n_particles=100, n_simulation=1000, algorithm="both_eps")
+    with pytest.raises(TypeError, match="closures"):
+        sb.sabc(lambda th: abs(th), prior, n_particles=100, n_simulation=1000)
+    with pytest.raises(RuntimeError, match="type"):
+        sb.sabc(model, prior, n_particles=100, n_simulation=1000, type="triple")
+
+
+def test_config_validation_in_the_library():
+    L = sb._lib
+    model, prior = sb.models.gauss_mean(1.0), sb.Normal(0, 1)
+    ok = dict(n_particles=100, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=1), resample=200, v=1.0, delta=0.1)
+    bad_model = sb.DeviceModel("not_registered", 1, 1, np.zeros(2))
+    with pytest.raises(sb.SABCError) as ei:
+        sb.Engine(bad_model, prior, **ok)
+    assert ei.value.code == -20
+    with pytest.raises(sb.SABCError) as ei:                               # prior length must match the model
+        sb.Engine(model, sb.product_distribution([sb.Normal(0, 1), sb.Uniform(0, 1)]), **ok)
+    assert ei.value.code == -20
+    with pytest.raises(sb.SABCError) as ei:
+        sb.Engine(model, prior, **{**ok, "n_particles": 2})
+    assert ei.value.code == -20
+    assert L.lib().sabc_destroy(None) == 0                                # idempotent on NULL
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail with SABC_ERR_CUDA instead of computing on the host."""
+    n = C.c_int(0)
+    rc = sb._lib.lib().sabc_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a CUDA device is present")
+    x = np.ones(4); out = np.zeros(4)
+    assert sb._lib.lib().sabc_detmath(0, sb._lib.ptr(x), 4, sb._lib.ptr(out)) == -30
+    with pytest.raises(sb.SABCError) as ei:
+        sb.Engine(sb.models.gauss_mean(1.0), sb.Normal(0, 1), n_particles=100, algorithm="single_eps",
+                  proposal=sb.DifferentialEvolution(n_para=1), resample=200, v=1.0, delta=0.1)
+    assert ei.value.code == -30
+    assert b"CUDA" in sb._lib.lib().sabc_last_error()
+
+
+def test_product_never_touches_the_oracle():
+    """the product tree must not reference oracle/ (parity would be void)."""
+    pkg = os.path.join(ROOT, "simulatedannealingabc.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl", ".jl")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower() or f in ("hooks.cu",) and "liboracle" not in text, f"{f} mentions the oracle"
+    out = subprocess.run(["ldd", sb._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_exchange_plan_is_consistent():
+    """multi-GPU resampling: the per-rank send/recv plans must tile every slice exactly once and match pairwise."""
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        for _ in range(50):
+            n_local = int(rng.integers(1, 5000))
+            counts = rng.multinomial(n_local * world, rng.dirichlet(np.ones(world) * rng.uniform(0.2, 50))).astype(np.int64)
+            plans = []
+            for me in range(world):
+                arrs = [np.zeros(world, dtype=np.int64) for _ in range(4)]
+                rc = sb._lib.lib().sabc_mg_exchange_plan(sb._lib.ptr(counts), world, n_local, me, *[sb._lib.ptr(a) for a in arrs])
+                assert rc == 0
+                plans.append(arrs)
+            for me in range(world):
+                s_off, s_cnt, r_off, r_cnt = plans[me]
+                assert s_cnt.sum() == counts[me] and r_cnt.sum() == n_local
+                filled = np.zeros(n_local, dtype=int)
+                for g in range(world):
+                    assert r_cnt[g] == plans[g][1][me]                     # what g sends to me is what I expect from g
+                    filled[r_off[g]:r_off[g] + r_cnt[g]] += 1
+                assert np.all(filled == 1)
+                sent = np.zeros(int(counts[me]), dtype=int)
+                for d in range(world):
+                    sent[s_off[d]:s_off[d] + s_cnt[d]] += 1
+                assert np.all(sent == 1)
+    bad = np.array([3, 3], dtype=np.int64); arrs = [np.zeros(2, dtype=np.int64) for _ in range(4)]
+    assert sb._lib.lib().sabc_mg_exchange_plan(sb._lib.ptr(bad), 2, 4, 0, *[sb._lib.ptr(a) for a in arrs]) == -20

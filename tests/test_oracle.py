@@ -1,0 +1,231 @@
+"""CPU tests of the ORACLE (no GPU): pins the C restatement against everything available offline --
+the reference's own ECDF assertions (test/runtests.jl:9-29), the restatement-derived known answers of SURVEY.md App. F
+(tests/golden/known_answers.json), the published Random123 Philox vectors, libm/mpmath for the deterministic math, an
+independent numpy restatement of the algorithm (statistical), and the analytic conjugate posterior."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import sabc_b200 as sb
+from helpers import model_cases, o_accept, o_detmath, o_ecdf_build, o_ecdf_eval
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))
+
+
+def ulps(a, b):
+    return np.abs(a - b) / np.spacing(np.abs(b))
+
+
+def test_detmath_against_libm():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.random(5000), 10 ** rng.uniform(-300, 300, 2000), [1.0, 2.0 ** -53, 1e-310]])
+    assert ulps(o_detmath(0, x), np.log(x)).max() <= 1.0
+    assert ob.lib().orc_log(0.0) == -math.inf and math.isnan(ob.lib().orc_log(-1.0))
+    x = np.concatenate([rng.uniform(-700, 700, 5000), rng.uniform(-1, 1, 2000)])
+    assert ulps(o_detmath(1, x), np.exp(x)).max() <= 1.0
+    assert ob.lib().orc_exp(-1000.0) == 0.0 and ob.lib().orc_exp(1000.0) == math.inf and ob.lib().orc_exp(0.0) == 1.0
+    import mpmath as mp
+    mp.mp.prec = 120
+    u = rng.random(1500)
+    sn = np.array([float(mp.sin(2 * mp.pi * mp.mpf(float(v)))) for v in u]); cs = np.array([float(mp.cos(2 * mp.pi * mp.mpf(float(v)))) for v in u])
+    assert np.abs(o_detmath(2, u) - sn).max() <= 1.5 * 2.0 ** -53
+    assert np.abs(o_detmath(3, u) - cs).max() <= 1.5 * 2.0 ** -53
+    k = np.concatenate([np.arange(40.0), [100.0, 1e4, 1e6]])
+    want = np.array([math.lgamma(v + 1) for v in k])
+    assert np.allclose(o_detmath(4, k), want, rtol=1e-14, atol=1e-15)
+
+
+def test_philox_random123_vectors():
+    for ctr, key, want in GOLDEN["philox4x32_10"]:
+        out = (C.c_uint32 * 4)()
+        ob.lib().orc_philox4x32_10((C.c_uint32 * 4)(*[int(c, 16) for c in ctr]), (C.c_uint32 * 2)(*[int(k, 16) for k in key]), out)
+        assert [f"{v:08x}" for v in out] == want
+
+
+def test_ecdf_reference_testset():
+    """test/runtests.jl:9-29, literally."""
+    rng = np.random.default_rng(1)
+    for data, scale in ((rng.random(100) * 4, 1.0), (np.array([1, 2, 2, 3, 3, 3.0]), 3.0), (np.array([1, 0, 2, 0, 3.0]), 3.0)):
+        k = o_ecdf_build(data)
+        assert o_ecdf_eval(k, 0.0)[0] <= math.sqrt(np.finfo(float).eps)
+        assert abs(o_ecdf_eval(k, np.inf)[0] - 1) < 1e-8
+        assert np.all(np.diff(o_ecdf_eval(k, np.sort(rng.random(100) * scale))) >= 0)
+
+
+def test_ecdf_known_answers():
+    for case in GOLDEN["build_cdf"]:
+        k = o_ecdf_build(np.array(case["data"], dtype=float))
+        got = o_ecdf_eval(k, np.array([math.inf if a == "Inf" else a for a in case["at"]], dtype=float))
+        assert np.allclose(got, case["want"], rtol=0, atol=2.3e-16), (got, case["want"])
+    k = o_ecdf_build(np.array([1, 2, 2, 3, 3, 3.0]))
+    assert np.array_equal(k, [0, 1, 2, 2, 3, 3, 3, 4.5])                  # [0; sort(x); 1.5 max]  cdf_estimators.jl:32-33
+    # searchsortedfirst-1 bracket: on a knot the LEFT interval is used; duplicates make G jump (App. A1)
+    assert o_ecdf_eval(k, 2.0)[0] == 1 / 7 + (1 / 7) / (2 - 1) * (2 - 1)
+    assert o_ecdf_eval(k, np.nextafter(2.0, 3))[0] > 3 / 7 - 1e-12
+    with pytest.raises(ValueError):
+        o_ecdf_build(np.zeros(4))
+    # k-th smallest positive distance maps to ~ k/(n+1)
+    x = np.random.default_rng(2).random(999) + 0.1
+    k = o_ecdf_build(x)
+    assert np.allclose(o_ecdf_eval(k, np.sort(x)), np.arange(1, 1000) / 1000, atol=1e-12)
+
+
+def test_epsilon_known_answers():
+    for ub, v, want in GOLDEN["update_epsilon_single_eps"]:
+        assert abs(ob.lib().orc_eps_single(ub, v) - want) <= 1e-9 * want
+        assert abs(ob.lib().orc_eps_single_bisect(ub, v) - want) <= 1e-9 * want
+    for ub, v, want in GOLDEN["update_epsilon_multi_eps"]:
+        a = np.array(ub, dtype=float); out = np.zeros(a.size)
+        assert ob.lib().orc_eps_multi(ob.p(a), a.size, float(v), ob.p(out)) == 0
+        assert np.allclose(out, want, rtol=1e-9)
+    assert ob.lib().orc_eps_single(1e-17, 1.0) == 0.0                     # ū <= eps() -> 0   (:93)
+    out = np.zeros(2)
+    assert ob.lib().orc_eps_multi(ob.p(np.array([0.2, 0.0])), 2, 1.0, ob.p(out)) == -5   # :107-109
+
+
+def test_epsilon_newton_equals_reference_bisection():
+    """the engine's Newton solve lands within 2 ulp of the literal bisection of Roots.find_zero (:93)"""
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        ub = 10 ** rng.uniform(-6, -0.31); v = 10 ** rng.uniform(-1.5, 1.5)
+        a, b = ob.lib().orc_eps_single(ub, v), ob.lib().orc_eps_single_bisect(ub, v)
+        assert abs(a - b) <= 8 * np.spacing(b), (ub, v, a, b)
+        assert abs(a * a + v * a ** 1.5 - ub * ub) <= 1e-13 * ub * ub
+
+
+def test_accept_rule_semantics():
+    """:314-329: L = (lp' - lp) + sum((u - u')/eps) + log_factor; accept iff log(U) < L; -Inf prior never accepts."""
+    rng = np.random.default_rng(4)
+    m, s = 20000, 3
+    uo, un = rng.random((m, s)), rng.random((m, s)); eps = np.array([0.2]); eps3 = np.array([0.2, 0.1, 0.4])
+    dlp = rng.normal(0, 1, m); lf = rng.normal(0, 0.2, m); U = rng.random(m)
+    for e in (eps, eps3):
+        want = np.log(U) < (dlp + ((uo - un) / e).sum(axis=1)) + lf
+        got = o_accept(uo, un, e, dlp, lf, U).astype(bool)
+        assert (got != want).mean() < 1e-4                                # libm vs det log can differ only on the threshold
+    dlp[:] = -np.inf
+    assert o_accept(uo, un, eps, dlp, lf, U).sum() == 0
+    assert o_accept(uo[:5], un[:5], eps, np.zeros(5), np.full(5, 1e3), np.zeros(5)).all()   # U = 0: log U = -Inf < L
+
+
+def test_poisson_sampler_distribution():
+    from scipy import stats
+    for lam in (0.3, 3.0, 9.9, 10.0, 47.0, 900.0, 1e5):
+        blk = C.c_uint32(0)
+        k = np.array([ob.lib().orc_poisson(lam, 5, i, 1, C.byref(C.c_uint32(0))) for i in range(40000)])
+        assert abs(k.mean() - lam) < 5 * math.sqrt(lam / k.size)
+        assert abs(k.var() - lam) < 0.05 * lam + 5 * lam * math.sqrt(2 / k.size)
+        if lam < 50:
+            hi = int(stats.poisson.ppf(0.9999, lam))
+            f = np.bincount(np.minimum(k, hi), minlength=hi + 1)
+            e = stats.poisson.pmf(np.arange(hi + 1), lam) * k.size; e[-1] += k.size - e.sum()
+            keep = e > 5
+            chi2 = ((f[keep] - e[keep]) ** 2 / e[keep]).sum()
+            assert stats.chi2.sf(chi2, keep.sum() - 1) > 1e-4, (lam, chi2)
+    assert ob.lib().orc_poisson(0.0, 5, 0, 1, C.byref(blk)) == 0 and blk.value == 0
+
+
+def test_normal_sampler_distribution():
+    from scipy import stats
+    z0, z1 = C.c_double(), C.c_double()
+    rng = np.random.default_rng(5)
+    zs = []
+    for a, b in rng.integers(0, 2 ** 63, (20000, 2), dtype=np.uint64) * 2:
+        ob.lib().orc_normal_pair(int(a), int(b), C.byref(z0), C.byref(z1)); zs += [z0.value, z1.value]
+    zs = np.array(zs)
+    assert stats.kstest(zs, "norm").pvalue > 1e-3 and abs(np.corrcoef(zs[::2], zs[1::2])[0, 1]) < 0.02
+
+
+def test_treesum_and_exact_mean():
+    rng = np.random.default_rng(6)
+    for n in (1, 255, 256, 257, 70000):
+        x = rng.lognormal(0, 2, n)
+        assert abs(ob.lib().orc_treesum(ob.p(x), n) - math.fsum(x)) <= 1e-13 * math.fsum(x)
+        u = rng.random(n); m = C.c_double()
+        ob.lib().orc_exact_mean_u(ob.p(u), n, C.byref(m))
+        assert abs(m.value - math.fsum(u) / n) <= 2e-16
+        ob.lib().orc_exact_mean_u(ob.p(u[::-1].copy()), n, C.byref(z := C.c_double()))
+        assert z.value == m.value                                          # order independent by construction
+
+
+def test_resampling_is_multinomial():
+    rng = np.random.default_rng(7)
+    n = 20000
+    u = np.asfortranarray(rng.random((n, 2)))
+    ubar = u.mean(axis=0); w = np.zeros(n); q = np.zeros(n, dtype=np.uint64)
+    ob.lib().orc_resample_weights(ob.p(u), n, 2, ob.p(ubar), 0.1, ob.p(w), ob.p(q))
+    assert np.allclose(w, np.exp(-(u[:, 0] * 0.1 / ubar[0] + u[:, 1] * 0.1 / ubar[1])), rtol=1e-14)      # :127
+    assert np.all(np.abs(q / 2.0 ** 32 - w) < 2.0 ** -32)
+    idx = np.zeros(n, dtype=np.int64)
+    ob.lib().orc_resample_indices(ob.p(q), n, 1, 1, ob.p(idx))
+    cnt = np.bincount(idx, minlength=n)
+    # group particles by weight decile: selected mass per decile follows the weight mass
+    order = np.argsort(w); dec = np.array_split(order, 10)
+    got = np.array([cnt[d].sum() for d in dec]) / n; want = np.array([w[d].sum() for d in dec]) / w.sum()
+    assert np.abs(got - want).max() < 0.01
+
+
+def test_counter_semantics():
+    """test/runtests.jl:56-78 with the same model shapes: 9 updates for N=100/n_sim=1000, 19 after another 1000, none for 50."""
+    for name in ("gauss_sample_d1s1", "gauss_sample_d2s2"):
+        model, prior = model_cases()[name]
+        for alg in ("multi_eps", "single_eps"):
+            o = ob.OracleEngine(model, prior, n_particles=100, algorithm=alg, proposal=sb.DifferentialEvolution(n_para=model.n_para),
+                                resample=200, v=1.0, delta=0.1)
+            o.init()
+            assert o.get_state()[1].tolist() == [100, 0, 1, 0]            # :213-223
+            o.update(900)
+            eps, cnt = o.get_state()
+            assert cnt[0] == 1000 and cnt[3] == 9 and np.all(eps < 1)
+            o.update(1000)
+            assert o.get_state()[1][3] == 19 and o.get_state()[1][0] == 2000
+            before = o.get_state()[1].copy(); nh = o.get_history()[0].shape[0]
+            o.update(50)
+            assert np.array_equal(o.get_state()[1], before) and o.get_history()[0].shape[0] == nh
+            assert nh == 1 + 9 + 10
+
+
+def test_errors():
+    model, prior = model_cases()["gauss_mean"]
+    kw = dict(n_particles=100, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=1), resample=200, delta=0.1)
+    o = ob.OracleEngine(model, prior, v=-0.1, **kw); o.init()
+    with pytest.raises(ob.OracleError) as ei:
+        o.update(1000)
+    assert ei.value.code == -2                                             # :261
+    kw2 = dict(kw); kw2["delta"] = -0.1
+    o = ob.OracleEngine(model, prior, v=1.0, **kw2)
+    with pytest.raises(ob.OracleError):                                    # weights with δ<0 still run at init; update refuses
+        o.init(); o.update(1000)
+
+
+def test_oracle_agrees_with_independent_numpy_restatement():
+    """Second, independent restatement (numpy RNG, np.interp ECDF, scipy brentq): the two implementations must agree
+    statistically on accept counts, resampling counts, eps and the posterior moments of C1."""
+    from ref_numpy_sabc import run
+    model, prior = model_cases()["gauss_mean"]
+    o = ob.OracleEngine(model, prior, n_particles=4000, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=1),
+                        resample=8000, v=1.0, delta=0.1, seed=3)
+    o.init(); o.update(150 * 4000)
+    th = o.get_population()[0][:, 0]; eps, cnt = o.get_state()
+    m, v, e, ubar, nacc, nres = run(N=4000, nsim=151 * 4000, seed=3)
+    assert abs(cnt[1] - nacc) < 0.05 * nacc and abs(cnt[2] - nres) <= 1
+    assert abs(math.log(eps[0] / e)) < 0.35
+    assert abs(th.mean() - m) < 0.03 and abs(th.var() - v) < 0.015
+
+
+def test_posterior_conjugate():
+    """C1 at slow annealing: mean/variance within 2 MC standard errors of N(10/11, 1/11)."""
+    model, prior = model_cases()["gauss_mean"]
+    ms, vs = [], []
+    for seed in range(6):
+        o = ob.OracleEngine(model, prior, n_particles=4000, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=1),
+                            resample=8000, v=0.02, delta=0.1, seed=100 + seed)
+        o.init(); o.update(400 * 4000)
+        th = o.get_population()[0][:, 0]; ms.append(th.mean()); vs.append(th.var())
+    assert abs(np.mean(ms) - 10 / 11) < 2 * np.std(ms, ddof=1) / math.sqrt(6)
+    assert abs(np.mean(vs) - 1 / 11) < 2 * np.std(vs, ddof=1) / math.sqrt(6)
