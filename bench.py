@@ -109,10 +109,10 @@ def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, ste
     import sabc_b200 as sb
     cores = ob.lib().orc_num_threads()
     kw = dict(algorithm=algorithm, proposal=sb.DifferentialEvolution(n_para=model.n_para), v=1.0, delta=0.1)
-    n_cal = min(max_particles, max(4 * cores, 2000))
+    n_cal = min(max_particles, max(256 * cores, 20000))
     o = ob.OracleEngine(model, prior, n_particles=n_cal, resample=2 * n_cal, **kw)
-    o.init(); o.update(2 * n_cal)
-    rate = 2 * n_cal / max(o.seconds, 1e-6)
+    o.init(); o.update(n_cal); o.update(3 * n_cal)
+    rate = 3 * n_cal / max(o.seconds, 1e-6)
     n = int(min(max_particles, max(n_cal, rate * target_seconds / max(steps + warmup, 1))))
     o = ob.OracleEngine(model, prior, n_particles=n, resample=2 * n, **kw)
     o.init()
