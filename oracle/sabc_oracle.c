@@ -193,35 +193,42 @@ static double normal32(uint64_t c) {
     return r * cs;
 }
 
-/* Poisson sampler: sequential-search inversion below 10, Hoermann's PTRS (1993) above. */
-static int64_t poisson(double lam, stream_t* st) {
+/* Poisson sampler (spec §3.3): one-uniform sequential-search inversion below 10, Hoermann's PTRS (1993) above,
+   with the acceptance tests rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one
+   Philox block (none when lam <= 0); poisson() repeats attempts until one accepts. */
+static int poisson_attempt(double lam, stream_t* st, int64_t* k_out) {
     uint64_t a, b;
-    if (!(lam > 0.0)) return 0;
+    if (!(lam > 0.0)) { *k_out = 0; return 1; }
+    stream_next(st, &a, &b);
     if (lam < 10.0) {
-        stream_next(st, &a, &b);
         double U = u53(a);
         double p = orc_exp(-lam), F = p;
         int64_t k = 0;
         while (U > F && k < 1024) { k++; p = (p * lam) / (double)k; F = F + p; }
-        return k;
+        *k_out = k;
+        return 1;
     }
     double slam = sqrt(lam);
     double bb = 0.931 + 2.53 * slam;
     double aa = -0.059 + 0.02483 * bb;
-    double vr = 0.9277 - 3.6224 / (bb - 2.0);
-    for (;;) {
-        stream_next(st, &a, &b);
-        double U = u53(a) - 0.5, V = u53(b);
-        double us = 0.5 - fabs(U);
-        double kf = floor((2.0 * aa / us + bb) * U + lam + 0.43);
-        if (us >= 0.07 && V <= vr) return (int64_t)kf;
-        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
-        double loglam = orc_log(lam);
-        double invalpha = 1.1239 + 1.1328 / (bb - 3.4);
-        double lhs = orc_log(V) + orc_log(invalpha) - orc_log(aa / (us * us) + bb);
-        double rhs = (-lam + kf * loglam) - orc_logfact(kf);
-        if (lhs <= rhs) return (int64_t)kf;
-    }
+    double U = u53(a) - 0.5, V = u53(b);
+    double us = 0.5 - fabs(U);
+    double r = 1.0 / us;
+    double kf = floor(((2.0 * aa) * r + bb) * U + lam + 0.43);
+    if (us >= 0.07 && (0.9277 - V) * (bb - 2.0) >= 3.6224) { *k_out = (int64_t)kf; return 1; }
+    if (kf < 0.0 || (us < 0.013 && V > us)) return 0;
+    double bm = bb - 3.4;
+    double num = V * (1.1239 * bm + 1.1328);
+    double den = bm * ((aa * r) * r + bb);
+    double lhs = orc_log(num / den);
+    double rhs = (-lam + kf * orc_log(lam)) - orc_logfact(kf);
+    if (lhs <= rhs) { *k_out = (int64_t)kf; return 1; }
+    return 0;
+}
+static int64_t poisson(double lam, stream_t* st) {
+    int64_t k;
+    while (!poisson_attempt(lam, st, &k)) {}
+    return k;
 }
 int64_t orc_poisson(double lam, uint64_t seed, uint32_t particle, uint64_t sweep, uint32_t* block_io) {
     stream_t st = { seed, particle, sweep, KIND_MODEL, *block_io };

@@ -377,6 +377,7 @@ static __global__ void k_finish(const FinishArgs a) {
         for (int j = 0; j < a.S; ++j) { ds->u_hi[j] = 0ull; ds->u_lo[j] = 0ull; }
         ds->n_acc_iter = 0ull;
         ds->resample_flag = 0;
+        ds->list_count[0] = ds->list_count[1] = ds->list_cursor[0] = ds->list_cursor[1] = 0u;
         ds->t += 1; ds->ix += 1;
     }
 }
@@ -423,6 +424,7 @@ static __global__ void k_begin(DevState* ds, long long t, long long n_pop, long 
     ds->t = t; ds->ix = 1; ds->n_pop = n_pop; ds->checkpoint = checkpoint; ds->rec = 0; ds->last_cp = 0;
     for (int j = 0; j < MAX_S; ++j) { ds->u_hi[j] = 0ull; ds->u_lo[j] = 0ull; }
     ds->n_acc_iter = 0ull; ds->resample_flag = 0;
+    ds->list_count[0] = ds->list_count[1] = ds->list_cursor[0] = ds->list_cursor[1] = 0u;
 }
 // Σu limbs of an existing u array (set_population, multi-GPU resampling)
 static __global__ void __launch_bounds__(CHUNK) k_sum_u(const double* u, int64_t ld, int64_t n, int S, unsigned long long* hi_out,

@@ -39,8 +39,8 @@ static void ensure_builtin_models() {
         r.push_back(ModelLaunchers<GaussSample<1, 2>>::vtable("gauss_sample_d1s2"));
         r.push_back(ModelLaunchers<GaussSample<2, 1>>::vtable("gauss_sample_d2s1"));
         r.push_back(ModelLaunchers<GaussSample<2, 2>>::vtable("gauss_sample_d2s2"));
-        r.push_back(ModelLaunchers<Logistic>::vtable("logistic"));
-        r.push_back(ModelLaunchers<SirTauLeap>::vtable("sir_tauleap"));
+        r.push_back(ModelLaunchers<Logistic>::vtable("logistic", 1));
+        r.push_back(ModelLaunchers<SirTauLeap>::vtable("sir_tauleap", 1));
     });
 }
 const ModelVTable* find_model(const char* name) {
@@ -90,6 +90,10 @@ struct sabc_engine {
     int top_doubles = 0;
     DevBuf<unsigned long long> b_q, b_tile_sum, b_tile_off;
     DevBuf<double> b_rho_part, b_scratch, b_rw_part, b_rw_sums, b_hist;
+    DevBuf<double> b_sp_theta, b_sp_lp, b_sp_lf;      // split path work list
+    DevBuf<uint32_t> b_sp_idx;
+    bool split = false;
+    int grid_simacc = 0, bps_simacc = 0;
     int64_t part_ld = 0, scratch_ld = 0, hist_cap = 0;
     int grid_update = 0, grid_aux = 0, bps_update = 0;
     size_t smem_update = 0;
@@ -159,6 +163,13 @@ static int ecdf_finalize(sabc_engine* e) {
     e->bps_update = bps;
     const int64_t groups = (e->n_local - e->n_local / 2 + CHUNK - 1) / CHUNK;
     e->grid_update = (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)bps * e->n_sm));
+    if (e->split) {
+        int b2 = 0;
+        SABC_CUDA(e->model->simacc_occupancy(e->smem_update, &b2));
+        if (b2 < 1) return set_error(SABC_ERR_CUDA, "simulate_accept kernel does not fit on an SM");
+        e->bps_simacc = b2;
+        e->grid_simacc = (int)std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)b2 * e->n_sm));
+    }
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     return 0;
 }
@@ -200,6 +211,52 @@ static int launch_update_half(sabc_engine* e, int half) {
     a.prior = e->prior; a.mp = e->mp;
     if (a.act_n <= 0) return 0;
     SABC_CUDA(e->model->launch_update(e->proposal, a, e->grid_update, e->smem_update, e->stream));
+    return 0;
+}
+
+static UpdateArgs make_update_args(sabc_engine* e, int half) {
+    UpdateArgs a{};
+    a.pop = e->pop;
+    halves(e, half, a.act_off, a.act_n, a.ina_off, a.ina_n);
+    a.particle_base = (uint32_t)e->offset;
+    a.half = half; a.seed = e->seed; a.ds = e->b_ds.p; a.ecdf = e->b_ecdf.p;
+    a.rho_part = e->b_rho_part.p + (int64_t)half * e->S * e->part_ld;
+    a.part_ld = e->part_ld; a.n_eps = e->n_eps; a.top_doubles = e->top_doubles;
+    a.prop0 = e->prop_par[0]; a.prop1 = e->prop_par[1];
+    a.prior = e->prior; a.mp = e->mp;
+    return a;
+}
+static SplitScratch make_split(sabc_engine* e) {
+    SplitScratch w{};
+    w.theta = e->b_sp_theta.p; w.lp = e->b_sp_lp.p; w.lf = e->b_sp_lf.p; w.idx = e->b_sp_idx.p;
+    w.count = &e->b_ds.p->list_count[0]; w.cursor = &e->b_ds.p->list_cursor[0];
+    w.cap = e->n_local - e->n_local / 2;
+    return w;
+}
+// split path, one half: propose + compact, then one simulation per lane over the work list
+static int launch_split_propose(sabc_engine* e, int half) {
+    const UpdateArgs a = make_update_args(e, half);
+    if (a.act_n <= 0) return 0;
+    const int64_t groups = (a.act_n + CHUNK - 1) / CHUNK;
+    SABC_CUDA(e->model->launch_propose(e->proposal, a, make_split(e), (int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), e->stream));
+    return 0;
+}
+static int launch_split_simacc(sabc_engine* e, int half) {
+    const UpdateArgs a = make_update_args(e, half);
+    if (a.act_n <= 0) return 0;
+    SABC_CUDA(e->model->launch_simacc(a, make_split(e), e->grid_simacc, e->smem_update, e->stream));
+    return 0;
+}
+static int launch_split_stats(sabc_engine* e) {
+    for (int half = 0; half < 2; ++half) {
+        int64_t off, n, t0, t1;
+        halves(e, half, off, n, t0, t1);
+        if (n <= 0) continue;
+        const int64_t groups = (n + CHUNK - 1) / CHUNK;
+        stats_kernel<<<(int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), CHUNK, 0, e->stream>>>(
+            e->pop, off, n, e->S, e->b_ds.p, e->b_rho_part.p + (int64_t)half * e->S * e->part_ld, e->part_ld);
+    }
+    SABC_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -258,13 +315,26 @@ static int launch_finish(sabc_engine* e) {
     return 0;
 }
 
-static int kernels_per_iteration(const sabc_engine* e) { return 2 + 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1; }
+static int kernels_per_iteration(const sabc_engine* e) { return (e->split ? 6 : 2) + 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1; }
+
+// the two half-sweeps (:304-332) in the fused or the split form
+static int enqueue_sweeps(sabc_engine* e) {
+    if (!e->split) {
+        SABC_TRY(launch_update_half(e, 0));
+        SABC_TRY(launch_update_half(e, 1));
+        return 0;
+    }
+    for (int half = 0; half < 2; ++half) {
+        SABC_TRY(launch_split_propose(e, half));
+        SABC_TRY(launch_split_simacc(e, half));
+    }
+    return launch_split_stats(e);
+}
 
 // one population update, single GPU: every launch is unconditional, the resampling kernels
 // return immediately unless the device-side trigger fired
 static int enqueue_iteration(sabc_engine* e) {
-    SABC_TRY(launch_update_half(e, 0));
-    SABC_TRY(launch_update_half(e, 1));
+    SABC_TRY(enqueue_sweeps(e));
     SABC_TRY(launch_post1(e, 1));
     SABC_TRY(launch_resample_local(e, 0));
     SABC_TRY(launch_update_proposal(e));
@@ -410,6 +480,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     e->v = c->v; e->delta = c->delta; e->resample = c->resample; e->seed = c->seed; e->flags = c->flags;
     if (e->flags & SABC_FLAG_TIME_KERNELS) e->flags |= SABC_FLAG_NO_GRAPH;
     if (world > 1) e->flags |= SABC_FLAG_NO_GRAPH;
+    e->split = model->heavy && !(e->flags & SABC_FLAG_FUSED);
     e->device = dev; e->model = model;
     for (int k = 0; k < c->n_model_par; ++k) e->mp.v[k] = c->model_par[k];
     e->prior.n = e->D;
@@ -434,6 +505,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     A(e->b_ttheta.alloc(n * e->D)); A(e->b_tu.alloc(n * e->S)); A(e->b_tlp.alloc(n));
     A(e->b_ds.alloc(1)); A(e->b_ecdf.alloc(MAX_S));
     A(e->b_q.alloc(n));
+    { const size_t cap = n - n / 2; A(e->b_sp_theta.alloc(cap * e->D)); A(e->b_sp_lp.alloc(cap)); A(e->b_sp_lf.alloc(cap)); A(e->b_sp_idx.alloc(cap)); }
     const int64_t n_tiles = ((int64_t)n + TILE - 1) / TILE;
     A(e->b_tile_sum.alloc((size_t)n_tiles)); A(e->b_tile_off.alloc((size_t)n_tiles));
     e->part_ld = ((int64_t)n + CHUNK - 1) / CHUNK + 1;
@@ -584,11 +656,13 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
                 for (int half = 0; half < 2 && rc == 0; ++half) {
                     cudaEvent_t a, b;
                     SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b));
+                    if (e->split) rc = launch_split_propose(e, half);
                     SABC_CUDA(cudaEventRecord(a, e->stream));
-                    rc = launch_update_half(e, half);
+                    if (rc == 0) rc = e->split ? launch_split_simacc(e, half) : launch_update_half(e, half);
                     SABC_CUDA(cudaEventRecord(b, e->stream));
                     kev.push_back(a); kev.push_back(b);
                 }
+                if (rc == 0 && e->split) rc = launch_split_stats(e);
                 if (rc == 0) rc = launch_post1(e, 1);
                 if (rc == 0) rc = launch_resample_local(e, 0);
                 if (rc == 0) rc = launch_update_proposal(e);
@@ -735,10 +809,10 @@ int sabc_get_timing(sabc_engine* e, sabc_timing* out) {
 }
 int sabc_update_kernel_info(sabc_engine* e, int* grid, int* block, int* smem_bytes, int* blocks_per_sm) {
     if (!e) return set_error(SABC_ERR_INVALID, "null engine");
-    if (grid) *grid = e->grid_update;
+    if (grid) *grid = e->split ? e->grid_simacc : e->grid_update;
     if (block) *block = CHUNK;
     if (smem_bytes) *smem_bytes = (int)e->smem_update;
-    if (blocks_per_sm) *blocks_per_sm = e->bps_update;
+    if (blocks_per_sm) *blocks_per_sm = e->split ? e->bps_simacc : e->bps_update;
     return 0;
 }
 

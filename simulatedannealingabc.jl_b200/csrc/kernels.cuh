@@ -28,6 +28,7 @@ struct DevState {
     long long ix, n_pop, checkpoint, rec, last_cp; // position inside the current update() call
     long long n_accept, n_resampling;
     int resample_flag, error_flag;
+    unsigned int list_count[2], list_cursor[2];    // split path: work-list length and fetch cursor per half
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -173,6 +174,18 @@ struct UpdateArgs {
     ModelPar mp;
 };
 
+// Work list of the split ("heavy model") path: proposals that passed the prior check, compacted so that every lane
+// of the simulation kernel has a simulation to run.
+struct SplitScratch {
+    double* theta;            // [D][cap] proposed θ′ in list order
+    double* lp;               // [cap] logpdf(prior, θ′)
+    double* lf;               // [cap] log_factor of the proposal
+    uint32_t* idx;            // [cap] local index (within the active half) of the particle
+    unsigned int* count;      // [2] entries per half
+    unsigned int* cursor;     // [2] dynamic work cursor of the simulation kernel per half
+    int64_t cap;
+};
+
 struct InitArgs {
     PopView pop;
     int64_t n;
@@ -294,6 +307,131 @@ __global__ void __launch_bounds__(CHUNK) update_half_kernel(const UpdateArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Split form of K4 for models whose simulation dominates (SIR, logistic): with DE/Stretch moves and bounded priors a
+// large share of the proposals fails the prior check (:314) and runs no simulation; inside the fused kernel those
+// lanes idle for the whole simulation of their warp.  propose_kernel therefore compacts the surviving proposals
+// into a work list and simulate_accept_kernel runs one simulation per lane over that list (warps fetch 32 items
+// at a time from a device-side cursor).  The Σu / Σρ / accept statistics are then taken by stats_kernel.
+// Results are identical to the fused kernel: every particle uses the same Philox streams and arithmetic.
+// ------------------------------------------------------------------------------------------------
+template <class M, int PROP>
+__global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, const SplitScratch w) {
+    constexpr int D = M::D;
+    __shared__ double s_chol[PROP == PROP_RW ? D * D : 1];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (PROP == PROP_RW) { for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k]; __syncthreads(); }
+    const uint64_t sweep = 2ull * (uint64_t)a.ds->t + (uint64_t)a.half;
+    const int64_t ld = a.pop.ld;
+    const int64_t n_groups = (a.act_n + CHUNK - 1) / CHUNK;
+    const InactiveGather<D> P{a.pop.theta + a.ina_off, ld};
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int64_t il = grp * CHUNK + tid;
+        bool ok = false;
+        double thp[D], lf = 0.0, lpp = 0.0;
+        if (il < a.act_n) {
+            const int64_t gi = a.act_off + il;
+            const uint32_t pid = a.particle_base + (uint32_t)gi;
+            double th[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) th[c] = a.pop.theta[c * ld + gi];
+            const CtrlWords cw = ctrl_words(a.seed, pid, sweep);
+            if (PROP == PROP_DE) propose_de<D>(th, P, a.ina_n, a.prop0, a.prop1, cw, thp, lf);
+            else if (PROP == PROP_STRETCH) propose_stretch<D>(th, P, a.ina_n, a.prop0, cw, thp, lf);
+            else propose_rw<D>(th, s_chol, a.seed, pid, sweep, thp, lf);
+            lpp = prior_logpdf<D>(a.prior, thp);
+            ok = lpp > -dinf();                                         // :314
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        unsigned base = 0;
+        if (lane == 0 && mask) base = atomicAdd(&w.count[a.half], (unsigned)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (ok) {
+            const int64_t q = base + __popc(mask & ((1u << lane) - 1u));
+#pragma unroll
+            for (int c = 0; c < D; ++c) w.theta[c * w.cap + q] = thp[c];
+            w.lp[q] = lpp; w.lf[q] = lf; w.idx[q] = (uint32_t)il;
+        }
+    }
+}
+
+template <class M>
+__global__ void __launch_bounds__(CHUNK) simulate_accept_kernel(const UpdateArgs a, const SplitScratch w) {
+    constexpr int D = M::D, S = M::S;
+    extern __shared__ double s_top[];
+    stage_ecdf_top(a.ecdf, S, s_top);
+    const int lane = threadIdx.x & 31;
+    const uint64_t sweep = 2ull * (uint64_t)a.ds->t + (uint64_t)a.half;
+    double eps[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) eps[j] = a.ds->eps[a.n_eps == 1 ? 0 : j];
+    const int64_t ld = a.pop.ld;
+    const unsigned n_items = w.count[a.half];
+    unsigned n_acc = 0;
+    for (;;) {
+        unsigned q0 = 0;
+        if (lane == 0) q0 = atomicAdd(&w.cursor[a.half], 32u);
+        q0 = __shfl_sync(0xffffffffu, q0, 0);
+        if (q0 >= n_items) break;
+        const unsigned q = q0 + lane;
+        if (q < n_items) {
+            const int64_t gi = a.act_off + (int64_t)w.idx[q];
+            const uint32_t pid = a.particle_base + (uint32_t)gi;
+            double thp[D], rp[S], up[S];
+#pragma unroll
+            for (int c = 0; c < D; ++c) thp[c] = w.theta[c * w.cap + q];
+            Stream st(a.seed, pid, sweep, KIND_MODEL);
+            M::sim(thp, a.mp, st, rp);                                  // :315
+            double Ssum = 0.0;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                up[j] = ecdf_eval(a.ecdf[j], s_top, rp[j]);             // :316
+                const double t = (a.pop.u[j * ld + gi] - up[j]) / eps[j];
+                Ssum = (j == 0) ? t : Ssum + t;
+            }
+            const double lpp = w.lp[q];
+            const double Lacc = ((lpp - a.pop.lp[gi]) + Ssum) + w.lf[q]; // :318-319
+            const uint64_t wD = Stream(a.seed, pid, sweep, KIND_CTRL).block(1).b;   // accept uniform: word D of the control stream
+            if (det_log(u53(wD)) < Lacc) {                              // :324-328
+#pragma unroll
+                for (int c = 0; c < D; ++c) a.pop.theta[c * ld + gi] = thp[c];
+#pragma unroll
+                for (int j = 0; j < S; ++j) { a.pop.u[j * ld + gi] = up[j]; a.pop.rho[j * ld + gi] = rp[j]; }
+                a.pop.lp[gi] = lpp;
+                n_acc++;
+            }
+        }
+    }
+    n_acc = __reduce_add_sync(0xffffffffu, n_acc);
+    if (lane == 0 && n_acc) atomicAdd(&a.ds->n_acc_iter, (unsigned long long)n_acc);
+}
+
+// Σu limbs and per-group ρ tree sums of one half after the split update (generic in S)
+static __global__ void __launch_bounds__(CHUNK) stats_kernel(PopView pop, int64_t off, int64_t n, int S, DevState* ds, double* rho_part,
+                                                      int64_t part_ld) {
+    __shared__ unsigned long long s_acc[2 * MAX_S];
+    __shared__ double s_w[8];
+    const int tid = threadIdx.x;
+    for (int k = tid; k < 2 * S; k += CHUNK) s_acc[k] = 0ull;
+    __syncthreads();
+    const int64_t n_groups = (n + CHUNK - 1) / CHUNK;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int64_t il = grp * CHUNK + tid;
+        const bool valid = il < n;
+        for (int j = 0; j < S; ++j) {
+            uint32_t hi = 0, lo = 0;
+            double r = 0.0;
+            if (valid) { u_limbs(pop.u[j * pop.ld + off + il], hi, lo); r = pop.rho[j * pop.ld + off + il]; }
+            const unsigned long long sh = warp_sum_u32(hi), sl = warp_sum_u32(lo);
+            if ((tid & 31) == 0) { atomicAdd(&s_acc[2 * j], sh); atomicAdd(&s_acc[2 * j + 1], sl); }
+            const double g = group256(r, s_w);
+            if (tid == 0) rho_part[j * part_ld + grp] = g;
+        }
+    }
+    __syncthreads();
+    if (tid < S) { atomicAdd(&ds->u_hi[tid], s_acc[2 * tid]); atomicAdd(&ds->u_lo[tid], s_acc[2 * tid + 1]); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1 init_prior_sim: θ ~ prior, ρ = f_dist(θ)  (src/SimulatedAnnealingABC.jl:172-179), negative
 // distance check (:185) and per-group ρ sums for ρ_history[1] (:180).
 // ------------------------------------------------------------------------------------------------
@@ -349,6 +487,10 @@ struct ModelVTable {
     cudaError_t (*launch_init)(const InitArgs&, int grid, cudaStream_t);
     cudaError_t (*launch_update)(int proposal, const UpdateArgs&, int grid, size_t smem, cudaStream_t);
     cudaError_t (*update_occupancy)(int proposal, size_t smem, int* blocks_per_sm);
+    int32_t heavy;            // 1: use the split path (propose -> compacted simulate+accept -> stats)
+    cudaError_t (*launch_propose)(int proposal, const UpdateArgs&, const SplitScratch&, int grid, cudaStream_t);
+    cudaError_t (*launch_simacc)(const UpdateArgs&, const SplitScratch&, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*simacc_occupancy)(size_t smem, int* blocks_per_sm);
     cudaError_t (*simulate)(const double* d_theta, int64_t n, int64_t ld, const ModelPar&, uint64_t seed,
                             uint32_t particle_base, uint64_t sweep, double* d_rho, cudaStream_t);
 };
@@ -394,13 +536,35 @@ struct ModelLaunchers {
             default: return cudaErrorInvalidValue;
         }
     }
+    static cudaError_t propose(int proposal, const UpdateArgs& a, const SplitScratch& w, int grid, cudaStream_t s) {
+        switch (proposal) {
+            case PROP_DE: propose_kernel<M, PROP_DE><<<grid, CHUNK, 0, s>>>(a, w); break;
+            case PROP_STRETCH: propose_kernel<M, PROP_STRETCH><<<grid, CHUNK, 0, s>>>(a, w); break;
+            case PROP_RW: propose_kernel<M, PROP_RW><<<grid, CHUNK, 0, s>>>(a, w); break;
+            default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
+    static cudaError_t simacc(const UpdateArgs& a, const SplitScratch& w, int grid, size_t smem, cudaStream_t s) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(simulate_accept_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        simulate_accept_kernel<M><<<grid, CHUNK, smem, s>>>(a, w);
+        return cudaGetLastError();
+    }
+    static cudaError_t simacc_occ(size_t smem, int* b) {
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, simulate_accept_kernel<M>, CHUNK, smem);
+    }
     static cudaError_t simulate(const double* th, int64_t n, int64_t ld, const ModelPar& mp, uint64_t seed,
                                 uint32_t pb, uint64_t sweep, double* rho, cudaStream_t s) {
         simulate_kernel<M><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(th, n, ld, mp, seed, pb, sweep, rho);
         return cudaGetLastError();
     }
-    static ModelVTable vtable(const char* name) {
-        return ModelVTable{name, M::D, M::S, &init, &update, &occupancy, &simulate};
+    static ModelVTable vtable(const char* name, int heavy = 0) {
+        ModelVTable v{};
+        v.name = name; v.n_para = M::D; v.n_stats = M::S;
+        v.launch_init = &init; v.launch_update = &update; v.update_occupancy = &occupancy; v.simulate = &simulate;
+        v.heavy = heavy; v.launch_propose = &propose; v.launch_simacc = &simacc; v.simacc_occupancy = &simacc_occ;
+        return v;
     }
 };
 #endif  // __CUDACC__

@@ -157,8 +157,7 @@ static int mg_resample(sabc_engine* e) {
 // one population update on this rank's slice
 static int mg_iteration(sabc_engine* e) {
     DevState* ds = e->b_ds.p;
-    SABC_TRY(launch_update_half(e, 0));
-    SABC_TRY(launch_update_half(e, 1));
+    SABC_TRY(enqueue_sweeps(e));
     SABC_TRY(launch_post1(e, 0));
     SABC_TRY(mg_reduce_iteration_sums(e));
     SABC_TRY(mg_allreduce_f64(e, &ds->rho_sum[0][0], 2 * MAX_S));

@@ -71,34 +71,42 @@ SABC_HD double normal32(uint64_t c) {
     return sqrt(-2.0 * det_log(u1)) * det_cos2pi(u2);
 }
 
-// Poisson(lam): one-uniform sequential-search inversion below 10, Hoermann's PTRS (1993) above.
-// The slow-path logarithms are evaluated lazily; the value drawn does not depend on that.
-SABC_HD int64_t poisson(double lam, Stream& st) {
-    if (!(lam > 0.0)) return 0;
+// Poisson(lam): one-uniform sequential-search inversion below 10, Hoermann's PTRS (1993) above, with
+// the acceptance tests rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one Philox
+// block (none when lam <= 0) and either returns a count or rejects; this is the unit the SIR kernel interleaves
+// across lanes so that a rejection in one lane does not stall the accepted lanes of its warp.
+SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
+    if (!(lam > 0.0)) { k_out = 0; return true; }
+    const U64x2 w = st.draw();
     if (lam < 10.0) {
-        const double U = u53(st.draw().a);
+        const double U = u53(w.a);
         double p = det_exp(-lam), F = p;
         int64_t k = 0;
         while (U > F && k < 1024) { k++; p = (p * lam) / (double)k; F = F + p; }
-        return k;
+        k_out = k;
+        return true;
     }
     const double slam = sqrt(lam);
     const double b = 0.931 + 2.53 * slam;
     const double a = -0.059 + 0.02483 * b;
-    const double vr = 0.9277 - 3.6224 / (b - 2.0);
-    for (;;) {
-        const U64x2 w = st.draw();
-        const double U = u53(w.a) - 0.5, V = u53(w.b);
-        const double us = 0.5 - fabs(U);
-        const double kf = floor((2.0 * a / us + b) * U + lam + 0.43);
-        if (us >= 0.07 && V <= vr) return (int64_t)kf;
-        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
-        const double loglam = det_log(lam);
-        const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
-        const double lhs = det_log(V) + det_log(invalpha) - det_log(a / (us * us) + b);
-        const double rhs = (-lam + kf * loglam) - det_logfact(kf);
-        if (lhs <= rhs) return (int64_t)kf;
-    }
+    const double U = u53(w.a) - 0.5, V = u53(w.b);
+    const double us = 0.5 - fabs(U);
+    const double r = 1.0 / us;
+    const double kf = floor(((2.0 * a) * r + b) * U + lam + 0.43);
+    if (us >= 0.07 && (0.9277 - V) * (b - 2.0) >= 3.6224) { k_out = (int64_t)kf; return true; }
+    if (kf < 0.0 || (us < 0.013 && V > us)) return false;
+    const double bm = b - 3.4;
+    const double num = V * (1.1239 * bm + 1.1328);
+    const double den = bm * ((a * r) * r + b);
+    const double lhs = det_log(num / den);
+    const double rhs = (-lam + kf * det_log(lam)) - det_logfact(kf);
+    if (lhs <= rhs) { k_out = (int64_t)kf; return true; }
+    return false;
+}
+SABC_HD int64_t poisson(double lam, Stream& st) {
+    int64_t k;
+    while (!poisson_attempt(lam, st, k)) {}
+    return k;
 }
 
 // exact, order-independent accumulation of u in [0,1]: u*2^62 split into two 31-bit limbs (§3.4)

@@ -244,6 +244,11 @@ struct Logistic {
 // C4: SIR tau-leap, θ = (β, γ, ι, φ).  par: pop, T, tau, obs_total, obs_peak, obs_tpeak
 struct SirTauLeap {
     static constexpr int D = 4, S = 3;
+    // Per step: n_inf ~ Poisson(β S I/pop τ) ∧ S, n_rec ~ Poisson(γ I τ) ∧ I, cases ~ Poisson(φ n_inf).  Written as a
+    // per-lane state machine over sampler ATTEMPTS (phase 0/1/2 = the three draws of a step): every loop trip each
+    // lane makes one attempt on its own current draw, so a PTRS rejection costs that lane one trip instead of
+    // stalling the whole warp.  The blocks a particle consumes, and hence its result, are those of the plain
+    // sequential loop (oracle/sabc_oracle.c model_sim).
     SABC_HD static void sim(const double (&th)[4], const ModelPar& mp, Stream& st, double (&rho)[3]) {
         const double pop = mp.v[0], tau = mp.v[2];
         const int T = (int)mp.v[1];
@@ -251,16 +256,27 @@ struct SirTauLeap {
         if (I < 0) I = 0;
         if (I > (int64_t)pop) I = (int64_t)pop;
         int64_t Sc = (int64_t)pop - I;
-        int64_t total = 0, peak = -1, tpeak = 0;
-        for (int t = 1; t <= T; ++t) {
-            const double li = (((th[0] * (double)Sc) * (double)I) / pop) * tau;
-            int64_t ninf = poisson(li, st); if (ninf > Sc) ninf = Sc;
-            const double lr = (th[1] * (double)I) * tau;
-            int64_t nrec = poisson(lr, st); if (nrec > I) nrec = I;
-            Sc -= ninf; I += ninf - nrec;
-            const int64_t c = poisson(th[3] * (double)ninf, st);
-            total += c;
-            if (c > peak) { peak = c; tpeak = t; }
+        int64_t total = 0, peak = -1, tpeak = 0, ninf = 0;
+        int t = 1, phase = 0;
+        double lam = (((th[0] * (double)Sc) * (double)I) / pop) * tau;
+        while (t <= T) {
+            int64_t k;
+            if (!poisson_attempt(lam, st, k)) continue;
+            if (phase == 0) {
+                ninf = k > Sc ? Sc : k;
+                lam = (th[1] * (double)I) * tau;
+                phase = 1;
+            } else if (phase == 1) {
+                const int64_t nrec = k > I ? I : k;
+                Sc -= ninf; I += ninf - nrec;
+                lam = th[3] * (double)ninf;
+                phase = 2;
+            } else {
+                total += k;
+                if (k > peak) { peak = k; tpeak = t; }
+                lam = (((th[0] * (double)Sc) * (double)I) / pop) * tau;
+                phase = 0; t++;
+            }
         }
         const double d0 = (double)total - mp.v[3], d1 = (double)peak - mp.v[4], d2 = (double)tpeak - mp.v[5];
         rho[0] = d0 * d0; rho[1] = d1 * d1; rho[2] = d2 * d2;

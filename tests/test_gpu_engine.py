@@ -82,6 +82,17 @@ def test_graph_and_direct_launch_agree(gpu):
     assert states[2][2]["kernel_ms"] > 0 and states[2][2]["kernel_launches"] == 30
 
 
+@pytest.mark.parametrize("name", ["sir_tauleap", "logistic"])
+@pytest.mark.parametrize("prop", ["de", "stretch", "rw"])
+def test_split_and_fused_kernels_agree(gpu, name, prop):
+    """simulation-heavy models run propose -> compacted simulate+accept -> stats; SABC_FLAG_FUSED forces the single fused
+    kernel.  Both must reproduce the oracle bit for bit."""
+    model, prior = model_cases()[name]
+    proposal = {"de": DE(model.n_para), "stretch": sb.StretchMove(), "rw": sb.RandomWalk(n_para=model.n_para)}[prop]
+    for flags in (0, sb.SABC_FLAG_FUSED, sb.SABC_FLAG_NO_GRAPH, sb.SABC_FLAG_FUSED | sb.SABC_FLAG_TIME_KERNELS):
+        run_pair(model, prior, 1500, 8, proposal=proposal, resample=1500, flags=flags)
+
+
 def test_checkpoint_history_striding(gpu):
     """history every k-th update plus a final record (:367-382)."""
     model, prior = model_cases()["gauss_mean"]
