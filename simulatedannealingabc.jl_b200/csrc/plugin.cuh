@@ -248,7 +248,7 @@ struct SirTauLeap {
     // per-lane state machine over sampler ATTEMPTS (phase 0/1/2 = the three draws of a step): every loop trip each
     // lane makes one attempt on its own current draw, so a PTRS rejection costs that lane one trip instead of
     // stalling the whole warp.  The blocks a particle consumes, and hence its result, are those of the plain
-    // sequential loop (oracle/sabc_oracle.c model_sim).
+    // sequential loop over steps and draws.
     SABC_HD static void sim(const double (&th)[4], const ModelPar& mp, Stream& st, double (&rho)[3]) {
         const double pop = mp.v[0], tau = mp.v[2];
         const int T = (int)mp.v[1];
