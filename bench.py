@@ -282,7 +282,8 @@ def main():
                 "how": "sabc_update_host per step: pinned host (theta,u,rho,eps,counters) -> device, one population update, device -> host"},
         "gpu_launches": int(t["total_launches"]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": f"update_half_kernel<{model.name}, DE>", "avg_kernel_ms": avg_kernel_ms, "kernel_launches": int(kernel_launches),
+                     "kernel": (f"simulate_accept_kernel<{model.name}> (split path: propose -> compacted simulate+accept -> stats)"
+                                if model.name in ("sir_tauleap", "logistic") else f"update_half_kernel<{model.name}, DE>"), "avg_kernel_ms": avg_kernel_ms, "kernel_launches": int(kernel_launches),
                      "kernel_share_of_step": kernel_ms / t["update_ms"] if time_kernels_live else None,
                      "algorithmic_bytes_per_update": bytes_per_update, "updates_per_launch": n_per_gpu / 2, "peak_source": peak_src,
                      "grid": kinfo, "timing": how,

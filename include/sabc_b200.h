@@ -82,6 +82,8 @@ typedef struct sabc_timing {
     int64_t kernel_launches;   /* number of update_half launches */
     int64_t total_launches;    /* all kernels launched by the loop */
     double  h2d_ms, d2h_ms;    /* host-buffer variants only */
+    double  resample_ms;       /* multi-GPU: host wall time inside the global resampling exchanges */
+    int64_t resample_events;
 } sabc_timing;
 
 /* ---- lifetime ---- */

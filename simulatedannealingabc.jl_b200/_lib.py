@@ -44,7 +44,8 @@ class Config(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("update_ms", C.c_double), ("kernel_ms", C.c_double), ("kernel_launches", C.c_int64),
-                ("total_launches", C.c_int64), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
+                ("total_launches", C.c_int64), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("resample_ms", C.c_double), ("resample_events", C.c_int64)]
 
 
 # every symbol include/sabc_b200.h declares: name -> (restype, argtypes)

@@ -10,6 +10,7 @@
 #include "nccl_dyn.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -523,6 +524,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     if (world > 1) {
         if (!c->nccl_unique_id) return fail(set_error(SABC_ERR_INVALID, "world_size > 1 needs nccl_unique_id"));
         int rc = e->comm.init(c->nccl_unique_id, e->rank, world);
+        if (rc == 0) rc = mg_warm_p2p(e);
         if (rc) return fail(rc);
     }
     *out = e;

@@ -86,6 +86,25 @@ static int launch_update_proposal_mg(sabc_engine* e) {
     return 0;
 }
 
+// Establish every send/recv connection once, at communicator creation: NCCL sets point-to-point channels up lazily per
+// direction, which otherwise costs hundreds of milliseconds inside the first resampling that needs a new direction.
+static int mg_warm_p2p(sabc_engine* e) {
+    NcclApi* nc = nccl_api();
+    MgScratch& s = e->mg;
+    SABC_CUDA(s.wall.ensure((size_t)2 * e->world));
+    SABC_CUDA(cudaMemsetAsync(s.wall.p, 0, sizeof(unsigned long long) * 2 * e->world, e->stream));
+    SABC_NCCL(nc->GroupStart());
+    for (int g = 0; g < e->world; ++g) {
+        if (g == e->rank) continue;
+        SABC_NCCL(nc->Send(s.wall.p + e->rank, 1, ncclUint64, g, e->comm.comm, e->stream));
+        SABC_NCCL(nc->Recv(s.wall.p + e->world + g, 1, ncclUint64, g, e->comm.comm, e->stream));
+    }
+    SABC_NCCL(nc->GroupEnd());
+    SABC_TRY(mg_allreduce_u64(e, s.wall.p, 1));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
 // exact global multinomial resampling over all ranks (resample_population, :124-137)
 static int mg_resample(sabc_engine* e) {
     MgScratch& s = e->mg;
@@ -166,7 +185,13 @@ static int mg_iteration(sabc_engine* e) {
     int flag = 0;
     SABC_CUDA(cudaMemcpyAsync(&flag, &ds->resample_flag, sizeof flag, cudaMemcpyDeviceToHost, e->stream));
     SABC_CUDA(cudaStreamSynchronize(e->stream));
-    if (flag) SABC_TRY(mg_resample(e));
+    if (flag) {
+        const auto t0 = std::chrono::steady_clock::now();
+        SABC_TRY(mg_resample(e));
+        SABC_CUDA(cudaStreamSynchronize(e->stream));
+        e->timing.resample_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        e->timing.resample_events += 1;
+    }
     SABC_TRY(launch_update_proposal_mg(e));
     SABC_TRY(launch_finish(e));
     return 0;

@@ -22,7 +22,8 @@ import sabc_b200 as sb
 from helpers import model_cases
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
-comm = sb.api._distributed_setup("torch")
+def new_comm():
+    return sb.api._distributed_setup("torch")     # every communicator needs a fresh ncclUniqueId
 
 def gather(a):
     out = [None] * world
@@ -34,6 +35,7 @@ for name, N, n_upd, prop in (("gauss_mean", 4000 * world, 30, "de"), ("gauss_sam
                              ("sir_tauleap", 2048 * world, 10, "de"), ("gauss_sample_d2s2", 2000 * world, 10, "rw")):
     model, prior = model_cases()[name]
     proposal = {"de": sb.DifferentialEvolution(n_para=model.n_para), "stretch": sb.StretchMove(), "rw": sb.RandomWalk(n_para=model.n_para)}[prop]
+    comm = new_comm()
     alg = "multi_eps" if model.n_stats > 1 and name != "sir_tauleap" else "single_eps"
     eng = sb.Engine(model, prior, n_particles=N, algorithm=alg, proposal=proposal, resample=N // 2, v=1.0, delta=0.1,
                     device=int(os.environ["LOCAL_RANK"]), rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2])
@@ -67,6 +69,7 @@ for name, N, n_upd, prop in (("gauss_mean", 4000 * world, 30, "de"), ("gauss_sam
 # resampling alone: run one forced global resampling through init on a tiny problem and check it copies existing particles
 model, prior = model_cases()["gauss_sample_d2s2"]
 N = 1024 * world
+comm = new_comm()
 eng = sb.Engine(model, prior, n_particles=N, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=2), resample=2 * N,
                 v=1.0, delta=0.1, device=int(os.environ["LOCAL_RANK"]), rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], seed=7)
 ref = sb.Engine(model, prior, n_particles=N, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=2), resample=2 * N,
@@ -89,6 +92,7 @@ if rank == 0:
 # posterior of C1 over the sharded population (slow annealing)
 model, prior = model_cases()["gauss_mean"]
 N = 4000 * world
+comm = new_comm()
 eng = sb.Engine(model, prior, n_particles=N, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=1), resample=2 * N,
                 v=0.02, delta=0.1, device=int(os.environ["LOCAL_RANK"]), rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], seed=11)
 eng.init(); eng.update(400 * N)
