@@ -287,7 +287,8 @@ def main():
                      "kernel_share_of_step": kernel_ms / t["update_ms"] if time_kernels_live else None,
                      "algorithmic_bytes_per_update": bytes_per_update, "updates_per_launch": n_per_gpu / 2, "peak_source": peak_src,
                      "grid": kinfo, "timing": how,
-                     "note": "the SIR kernel is FP64/INT-issue and latency bound, not HBM bound (DESIGN.md §5); see profiles/ for pipe utilisation"},
+                     "note": ("simulation-heavy model: FP64/INT-issue and divergence bound, not HBM bound (DESIGN.md section 4); profiles/ holds the pipe utilisation"
+                              if model.name in ("sir_tauleap", "logistic") else "state streaming + ECDF leaf sectors (DESIGN.md section 4)")},
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
