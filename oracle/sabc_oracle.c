@@ -204,7 +204,7 @@ static int poisson_attempt(double lam, stream_t* st, int64_t* k_out) {
         double U = u53(a);
         double p = orc_exp(-lam), F = p;
         int64_t k = 0;
-        while (U > F && k < 1024) { k++; p = (p * lam) / (double)k; F = F + p; }
+        while (U > F && k < 1024) { k++; p = (p * lam) * (1.0 / (double)k); F = F + p; }
         *k_out = k;
         return 1;
     }
@@ -540,13 +540,14 @@ static int model_sim(int32_t id, int32_t d, int32_t s, const double* mp, const d
         return 0; }
     case ORC_MODEL_SIR: {               /* par: pop, T, tau, obs_total, obs_peak, obs_tpeak; theta = (β, γ, ι, φ) */
         double pop = mp[0]; int T = (int)mp[1]; double tau = mp[2];
+        double inv_pop = 1.0 / pop;
         int64_t I = (int64_t)floor(th[2] * pop + 0.5);
         if (I < 0) I = 0;
         if (I > (int64_t)pop) I = (int64_t)pop;
         int64_t S = (int64_t)pop - I;
         int64_t total = 0, peak = -1, tpeak = 0;
         for (int t = 1; t <= T; ++t) {
-            double li = (((th[0] * (double)S) * (double)I) / pop) * tau;
+            double li = (((th[0] * (double)S) * (double)I) * inv_pop) * tau;
             int64_t ninf = poisson(li, &st); if (ninf > S) ninf = S;
             double lr = (th[1] * (double)I) * tau;
             int64_t nrec = poisson(lr, &st); if (nrec > I) nrec = I;

@@ -71,6 +71,34 @@ SABC_HD double normal32(uint64_t c) {
     return sqrt(-2.0 * det_log(u1)) * det_cos2pi(u2);
 }
 
+// correctly rounded reciprocal: 1.0/x on the host, the cheaper MUFU-seeded __drcp_rn on the device (same bits)
+SABC_HD double drcp(double x) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
+// 1/k, correctly rounded, for the inversion loop: a 64-entry table on the device (the loop runs with few live lanes,
+// so a broadcast-style constant read beats the ~10-instruction reciprocal), the division itself elsewhere
+#if defined(__CUDACC__)
+__constant__ double c_rcp_int[64] = {
+    0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
+    1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
+    1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37,
+    1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49,
+    1.0 / 50, 1.0 / 51, 1.0 / 52, 1.0 / 53, 1.0 / 54, 1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61,
+    1.0 / 62, 1.0 / 63};
+#endif
+SABC_HD double rcp_int(int k) {
+#if defined(__CUDA_ARCH__)
+    return k < 64 ? c_rcp_int[k] : __drcp_rn((double)k);
+#else
+    return 1.0 / (double)k;
+#endif
+}
+
 // Poisson(lam): one-uniform sequential-search inversion below 10, Hoermann's PTRS (1993) above, with
 // the acceptance tests rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one Philox
 // block (none when lam <= 0) and either returns a count or rejects; this is the unit the SIR kernel interleaves
@@ -81,8 +109,8 @@ SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
     if (lam < 10.0) {
         const double U = u53(w.a);
         double p = det_exp(-lam), F = p;
-        int64_t k = 0;
-        while (U > F && k < 1024) { k++; p = (p * lam) / (double)k; F = F + p; }
+        int k = 0;
+        while (U > F && k < 1024) { k++; p = (p * lam) * rcp_int(k); F = F + p; }         // p_k = p_{k-1} λ (1/k)
         k_out = k;
         return true;
     }
@@ -91,7 +119,7 @@ SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
     const double a = -0.059 + 0.02483 * b;
     const double U = u53(w.a) - 0.5, V = u53(w.b);
     const double us = 0.5 - fabs(U);
-    const double r = 1.0 / us;
+    const double r = drcp(us);
     const double kf = floor(((2.0 * a) * r + b) * U + lam + 0.43);
     if (us >= 0.07 && (0.9277 - V) * (b - 2.0) >= 3.6224) { k_out = (int64_t)kf; return true; }
     if (kf < 0.0 || (us < 0.013 && V > us)) return false;

@@ -251,6 +251,7 @@ struct SirTauLeap {
     // sequential loop over steps and draws.
     SABC_HD static void sim(const double (&th)[4], const ModelPar& mp, Stream& st, double (&rho)[3]) {
         const double pop = mp.v[0], tau = mp.v[2];
+        const double inv_pop = drcp(pop);
         const int T = (int)mp.v[1];
         int64_t I = (int64_t)floor(th[2] * pop + 0.5);
         if (I < 0) I = 0;
@@ -258,7 +259,7 @@ struct SirTauLeap {
         int64_t Sc = (int64_t)pop - I;
         int64_t total = 0, peak = -1, tpeak = 0, ninf = 0;
         int t = 1, phase = 0;
-        double lam = (((th[0] * (double)Sc) * (double)I) / pop) * tau;
+        double lam = (((th[0] * (double)Sc) * (double)I) * inv_pop) * tau;
         while (t <= T) {
             int64_t k;
             if (!poisson_attempt(lam, st, k)) continue;
@@ -274,7 +275,7 @@ struct SirTauLeap {
             } else {
                 total += k;
                 if (k > peak) { peak = k; tpeak = t; }
-                lam = (((th[0] * (double)Sc) * (double)I) / pop) * tau;
+                lam = (((th[0] * (double)Sc) * (double)I) * inv_pop) * tau;
                 phase = 0; t++;
             }
         }
