@@ -73,6 +73,7 @@ typedef struct sabc_config {
 
 #define SABC_FLAG_NO_GRAPH      1u  /* launch kernels directly instead of replaying a CUDA graph */
 #define SABC_FLAG_TIME_KERNELS  2u  /* record CUDA events around every update_half / simulate_accept launch (implies NO_GRAPH) */
+#define SABC_FLAG_NO_PIPELINE   8u  /* sabc_update_host: upload, update, download strictly one after the other */
 #define SABC_FLAG_FUSED         4u  /* always use the fused update_half kernel, also for simulation-heavy models */
 
 /* timing of the last sabc_update(), measured with CUDA events on the engine's stream */
@@ -81,7 +82,8 @@ typedef struct sabc_timing {
     double  kernel_ms;         /* sum over update_half launches (only with SABC_FLAG_TIME_KERNELS) */
     int64_t kernel_launches;   /* number of update_half launches */
     int64_t total_launches;    /* all kernels launched by the loop */
-    double  h2d_ms, d2h_ms;    /* host-buffer variants only */
+    double  h2d_ms, d2h_ms;    /* host-buffer call: duration of the upload / of the final download (they overlap the updates) */
+    double  host_ms;           /* host-buffer call: first byte up to last byte down, CUDA events */
     double  resample_ms;       /* multi-GPU: host wall time inside the global resampling exchanges */
     int64_t resample_events;
 } sabc_timing;

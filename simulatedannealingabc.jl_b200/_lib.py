@@ -17,6 +17,7 @@ c_int32_p = C.POINTER(C.c_int32)
 SABC_FLAG_NO_GRAPH = 1
 SABC_FLAG_TIME_KERNELS = 2
 SABC_FLAG_FUSED = 4
+SABC_FLAG_NO_PIPELINE = 8
 
 ERR_NAMES = {
     -1: "NSIM_TOO_SMALL", -2: "BAD_V", -3: "BAD_DELTA", -4: "NEG_DISTANCE", -5: "UBAR_ZERO", -6: "BAD_ALGORITHM",
@@ -44,7 +45,7 @@ class Config(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("update_ms", C.c_double), ("kernel_ms", C.c_double), ("kernel_launches", C.c_int64),
-                ("total_launches", C.c_int64), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("total_launches", C.c_int64), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("host_ms", C.c_double),
                 ("resample_ms", C.c_double), ("resample_events", C.c_int64)]
 
 

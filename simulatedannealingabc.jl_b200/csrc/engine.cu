@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -95,6 +96,13 @@ struct sabc_engine {
     DevBuf<uint32_t> b_sp_idx;
     bool split = false;
     int grid_simacc = 0, bps_simacc = 0;
+
+    // per-call hooks of the sweeps: kernel timing events and the copy/compute pipeline of the host-buffer call
+    std::vector<cudaEvent_t>* kev = nullptr;           // event pairs around the dominant kernel of each half
+    cudaEvent_t pipe_wait_half1 = nullptr;             // second half-sweep waits for the rest of the upload
+    cudaEvent_t pipe_rec_half0 = nullptr;              // recorded after the first half-sweep (early download of half 0)
+    std::function<int()> pipe_on_half0;                // enqueues that download once the event is in the stream
+    cudaStream_t s_in = nullptr, s_out = nullptr;
     int64_t part_ld = 0, scratch_ld = 0, hist_cap = 0;
     int grid_update = 0, grid_aux = 0, bps_update = 0;
     size_t smem_update = 0;
@@ -113,6 +121,8 @@ struct sabc_engine {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (auto* b : ecdf_bufs) delete b;
         comm.destroy();
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -318,18 +328,24 @@ static int launch_finish(sabc_engine* e) {
 
 static int kernels_per_iteration(const sabc_engine* e) { return (e->split ? 6 : 2) + 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1; }
 
-// the two half-sweeps (:304-332) in the fused or the split form
+// the two half-sweeps (:304-332) in the fused or the split form, with the optional per-call hooks
 static int enqueue_sweeps(sabc_engine* e) {
-    if (!e->split) {
-        SABC_TRY(launch_update_half(e, 0));
-        SABC_TRY(launch_update_half(e, 1));
-        return 0;
-    }
     for (int half = 0; half < 2; ++half) {
-        SABC_TRY(launch_split_propose(e, half));
-        SABC_TRY(launch_split_simacc(e, half));
+        if (half == 1 && e->pipe_wait_half1) SABC_CUDA(cudaStreamWaitEvent(e->stream, e->pipe_wait_half1, 0));
+        if (e->split) SABC_TRY(launch_split_propose(e, half));
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (e->kev) {
+            SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b));
+            SABC_CUDA(cudaEventRecord(a, e->stream));
+        }
+        if (e->split) SABC_TRY(launch_split_simacc(e, half)); else SABC_TRY(launch_update_half(e, half));
+        if (e->kev) { SABC_CUDA(cudaEventRecord(b, e->stream)); e->kev->push_back(a); e->kev->push_back(b); }
+        if (half == 0 && e->pipe_rec_half0) {
+            SABC_CUDA(cudaEventRecord(e->pipe_rec_half0, e->stream));
+            if (e->pipe_on_half0) SABC_TRY(e->pipe_on_half0());
+        }
     }
-    return launch_split_stats(e);
+    return e->split ? launch_split_stats(e) : 0;
 }
 
 // one population update, single GPU: every launch is unconditional, the resampling kernels
@@ -647,32 +663,27 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
     std::vector<cudaEvent_t> kev;
     const bool time_kernels = (e->flags & SABC_FLAG_TIME_KERNELS) != 0;
     int rc = 0;
+    cudaEvent_t pipe_rec_pending = e->pipe_rec_half0;
+    const bool piped = e->pipe_wait_half1 || e->pipe_rec_half0;
     if (e->world > 1) {
         SABC_CUDA(cudaEventRecord(ev0, e->stream));
-        for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) rc = mg_iteration(e);
-        SABC_CUDA(cudaEventRecord(ev1, e->stream));
-    } else if (e->flags & SABC_FLAG_NO_GRAPH) {
-        SABC_CUDA(cudaEventRecord(ev0, e->stream));
+        if (time_kernels) e->kev = &kev;
         for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) {
-            if (time_kernels) {
-                for (int half = 0; half < 2 && rc == 0; ++half) {
-                    cudaEvent_t a, b;
-                    SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b));
-                    if (e->split) rc = launch_split_propose(e, half);
-                    SABC_CUDA(cudaEventRecord(a, e->stream));
-                    if (rc == 0) rc = e->split ? launch_split_simacc(e, half) : launch_update_half(e, half);
-                    SABC_CUDA(cudaEventRecord(b, e->stream));
-                    kev.push_back(a); kev.push_back(b);
-                }
-                if (rc == 0 && e->split) rc = launch_split_stats(e);
-                if (rc == 0) rc = launch_post1(e, 1);
-                if (rc == 0) rc = launch_resample_local(e, 0);
-                if (rc == 0) rc = launch_update_proposal(e);
-                if (rc == 0) rc = launch_finish(e);
-            } else {
-                rc = enqueue_iteration(e);
-            }
+            if (ix == 1) e->pipe_wait_half1 = nullptr;
+            e->pipe_rec_half0 = (ix == n_pop - 1) ? pipe_rec_pending : nullptr;
+            rc = mg_iteration(e);
         }
+        e->kev = nullptr; e->pipe_wait_half1 = nullptr; e->pipe_rec_half0 = nullptr;
+        SABC_CUDA(cudaEventRecord(ev1, e->stream));
+    } else if ((e->flags & SABC_FLAG_NO_GRAPH) || piped) {
+        SABC_CUDA(cudaEventRecord(ev0, e->stream));
+        if (time_kernels) e->kev = &kev;
+        for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) {
+            if (ix == 1) e->pipe_wait_half1 = nullptr;                                  // upload overlap: first update only
+            e->pipe_rec_half0 = (ix == n_pop - 1) ? pipe_rec_pending : nullptr;         // early download: last update only
+            rc = enqueue_iteration(e);
+        }
+        e->kev = nullptr; e->pipe_wait_half1 = nullptr; e->pipe_rec_half0 = nullptr;
         SABC_CUDA(cudaEventRecord(ev1, e->stream));
     } else {
         if (!e->graph_exec) {
@@ -742,26 +753,109 @@ int sabc_set_population(sabc_engine* e, const double* theta, const double* u, co
     return 0;
 }
 
+// Column-wise copies of the row range [r0, r1) of a column-major n x ncol matrix
+static int copy_rows(double* dst, const double* src, int64_t n, int ncol, int64_t r0, int64_t r1, cudaMemcpyKind kind, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    if (r0 == 0 && r1 == n) { SABC_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * ncol * sizeof(double), kind, st)); return 0; }
+    for (int c = 0; c < ncol; ++c)
+        SABC_CUDA(cudaMemcpyAsync(dst + (int64_t)c * n + r0, src + (int64_t)c * n + r0, (size_t)(r1 - r0) * sizeof(double), kind, st));
+    return 0;
+}
+
+// update_population!(::SABCresult) with the result held in host buffers.  For large slices the transfers are pipelined
+// with the two half-sweeps: the first sweep starts as soon as theta and the first half of u, rho have arrived, the rest
+// of the upload overlaps it; the first half is downloaded while the second sweep runs.
 int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, double* eps, int64_t counters[4],
                      int64_t n_simulation, int64_t checkpoint_history) {
     if (!e) return set_error(SABC_ERR_INVALID, "null engine");
-    cudaEvent_t a, b, c, d;
+    if (!theta || !u || !rho || !eps || !counters) return set_error(SABC_ERR_INVALID, "null argument");
     SABC_CUDA(cudaSetDevice(e->device));
+    const int64_t n = e->n_local, h0 = n / 2, n_pop = n_simulation / e->N;
+    const bool pipe = n_pop >= 1 && n >= 32768 && !(e->flags & SABC_FLAG_NO_PIPELINE) && e->top_doubles > 0 &&
+                      e->v > 0.0 && e->delta > 0.0;
+    cudaEvent_t a, b, c, d;
     SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b)); SABC_CUDA(cudaEventCreate(&c)); SABC_CUDA(cudaEventCreate(&d));
-    SABC_CUDA(cudaEventRecord(a, e->stream));
-    SABC_TRY(sabc_set_population(e, theta, u, rho, eps, counters));
-    SABC_CUDA(cudaEventRecord(b, e->stream));
-    SABC_TRY(sabc_update(e, n_simulation, checkpoint_history));
-    SABC_CUDA(cudaEventRecord(c, e->stream));
-    SABC_TRY(sabc_get_population(e, theta, u, rho));
-    SABC_TRY(sabc_get_state(e, eps, counters));
-    SABC_CUDA(cudaEventRecord(d, e->stream));
-    SABC_CUDA(cudaEventSynchronize(d));
-    float t1 = 0, t2 = 0;
-    cudaEventElapsedTime(&t1, a, b); cudaEventElapsedTime(&t2, c, d);
-    e->timing.h2d_ms = t1; e->timing.d2h_ms = t2;
-    cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d);
-    return 0;
+    auto cleanup = [&] { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); };
+    int rc = 0;
+    if (!pipe) {
+        SABC_CUDA(cudaEventRecord(a, e->stream));
+        rc = sabc_set_population(e, theta, u, rho, eps, counters);
+        if (!rc) { SABC_CUDA(cudaEventRecord(b, e->stream)); rc = sabc_update(e, n_simulation, checkpoint_history); }
+        if (!rc) { SABC_CUDA(cudaEventRecord(c, e->stream)); rc = sabc_get_population(e, theta, u, rho); }
+        if (!rc) rc = sabc_get_state(e, eps, counters);
+        if (!rc) {
+            SABC_CUDA(cudaEventRecord(d, e->stream));
+            SABC_CUDA(cudaEventSynchronize(d));
+            float t1 = 0, t2 = 0, t3 = 0;
+            cudaEventElapsedTime(&t1, a, b); cudaEventElapsedTime(&t2, c, d); cudaEventElapsedTime(&t3, a, d);
+            e->timing.h2d_ms = t1; e->timing.d2h_ms = t2; e->timing.host_ms = t3;
+        }
+        cleanup();
+        return rc;
+    }
+    if (!e->s_in) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    if (!e->s_out) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    cudaEvent_t evA, evB, evS0;
+    SABC_CUDA(cudaEventCreateWithFlags(&evA, cudaEventDisableTiming)); SABC_CUDA(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
+    SABC_CUDA(cudaEventCreateWithFlags(&evS0, cudaEventDisableTiming));
+    auto cleanup2 = [&] { cudaEventDestroy(evA); cudaEventDestroy(evB); cudaEventDestroy(evS0); cleanup(); };
+    const auto H2D = cudaMemcpyHostToDevice; const auto D2H = cudaMemcpyDeviceToHost;
+    // upload, part A (what the first half-sweep touches): theta, rows [0,h0) of u and rho
+    SABC_CUDA(cudaEventRecord(a, e->s_in));
+    rc = copy_rows(e->pop.theta, theta, n, e->D, 0, n, H2D, e->s_in);
+    if (!rc) rc = copy_rows(e->pop.u, u, n, e->S, 0, h0, H2D, e->s_in);
+    if (!rc) rc = copy_rows(e->pop.rho, rho, n, e->S, 0, h0, H2D, e->s_in);
+    if (!rc) { SABC_CUDA(cudaEventRecord(evA, e->s_in)); }
+    // part B: the second half of u and rho, overlapping the first half-sweep
+    if (!rc) rc = copy_rows(e->pop.u, u, n, e->S, h0, n, H2D, e->s_in);
+    if (!rc) rc = copy_rows(e->pop.rho, rho, n, e->S, h0, n, H2D, e->s_in);
+    if (rc) { cleanup2(); return rc; }
+    SABC_CUDA(cudaEventRecord(evB, e->s_in));
+    SABC_CUDA(cudaEventRecord(b, e->s_in));
+    // state scalars + cached log-prior once theta is there
+    SABC_CUDA(cudaStreamWaitEvent(e->stream, evA, 0));
+    k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, n, e->D, e->prior);
+    for (int k = 0; k < e->n_eps; ++k) e->eps[k] = eps[k];
+    e->n_simulation = counters[0]; e->n_accept = counters[1]; e->n_resampling = counters[2]; e->n_population_updates = counters[3];
+    SABC_CUDA(cudaMemcpyAsync(&e->b_ds.p->eps[0], e->eps, sizeof(double) * e->n_eps, H2D, e->stream));
+    k_set_counters<<<1, 1, 0, e->stream>>>(e->b_ds.p, e->n_accept, e->n_resampling);
+    SABC_CUDA(cudaGetLastError());
+    e->initialised = true;
+    const int64_t n_res_before = e->n_resampling;
+    // hooks: second half-sweep of the first update waits for part B; after the first half-sweep of the last update
+    // rows [0,h0) are final (unless a resampling follows) and go home while the second half-sweep runs
+    e->pipe_wait_half1 = evB;
+    e->pipe_rec_half0 = evS0;
+    e->pipe_on_half0 = [&]() -> int {
+        SABC_CUDA(cudaStreamWaitEvent(e->s_out, evS0, 0));
+        SABC_TRY(copy_rows(theta, e->pop.theta, n, e->D, 0, h0, D2H, e->s_out));
+        SABC_TRY(copy_rows(u, e->pop.u, n, e->S, 0, h0, D2H, e->s_out));
+        return copy_rows(rho, e->pop.rho, n, e->S, 0, h0, D2H, e->s_out);
+    };
+    rc = sabc_update(e, n_simulation, checkpoint_history);          // blocks until the updates are done
+    e->pipe_wait_half1 = nullptr; e->pipe_rec_half0 = nullptr; e->pipe_on_half0 = nullptr;
+    const sabc_timing t_upd = e->timing;
+    if (!rc) {
+        SABC_CUDA(cudaEventRecord(c, e->s_out));
+        const bool resampled = e->n_resampling != n_res_before;     // theta, u of every row changed: fetch them again
+        rc = copy_rows(theta, e->pop.theta, n, e->D, resampled ? 0 : h0, n, D2H, e->s_out);
+        if (!rc) rc = copy_rows(u, e->pop.u, n, e->S, resampled ? 0 : h0, n, D2H, e->s_out);
+        if (!rc) rc = copy_rows(rho, e->pop.rho, n, e->S, h0, n, D2H, e->s_out);
+        if (!rc) rc = sabc_get_state(e, eps, counters);
+    }
+    if (!rc) {
+        SABC_CUDA(cudaEventRecord(d, e->s_out));
+        SABC_CUDA(cudaEventSynchronize(d));
+        SABC_CUDA(cudaStreamSynchronize(e->s_in));
+        float t1 = 0, t2 = 0, t3 = 0;
+        cudaEventElapsedTime(&t1, a, b); cudaEventElapsedTime(&t2, c, d); cudaEventElapsedTime(&t3, a, d);
+        e->timing = t_upd;
+        e->timing.h2d_ms = t1; e->timing.d2h_ms = t2; e->timing.host_ms = t3;
+    } else {
+        cudaStreamSynchronize(e->s_in); cudaStreamSynchronize(e->s_out);
+    }
+    cleanup2();
+    return rc;
 }
 
 int sabc_get_state(sabc_engine* e, double* eps, int64_t counters[4]) {

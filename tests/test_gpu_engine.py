@@ -136,6 +136,37 @@ def test_host_round_trip(gpu):
     assert t["h2d_ms"] > 0 and t["d2h_ms"] > 0
 
 
+@pytest.mark.parametrize("name,n_upd,resample", [("gauss_sample_d2s2", 1, 10**9), ("gauss_sample_d2s2", 3, 20000), ("sir_tauleap", 2, 15000),
+                                                  ("gauss_mean", 4, 30000)])
+def test_host_round_trip_pipelined(gpu, name, n_upd, resample):
+    """large slices overlap the transfers with the half-sweeps (sabc_update_host); the result must equal both the strictly
+    sequential call (SABC_FLAG_NO_PIPELINE) and the oracle, also when a resampling falls into the last update."""
+    model, prior = model_cases()[name]
+    N = 70_001
+    alg = "multi_eps" if name == "gauss_sample_d2s2" else "single_eps"
+    kw = dict(n_particles=N, algorithm=alg, proposal=DE(model.n_para), resample=resample, v=1.0, delta=0.1)
+    src = sb.Engine(model, prior, **kw); src.init(); src.update(2 * N)
+    orc = ob.OracleEngine(model, prior, **kw); orc.init(); orc.update(2 * N); orc.update(n_upd * N)
+    th, u, rho = src.get_population(); eps, cnt = src.get_state()
+    outs = []
+    for flags in (0, sb.SABC_FLAG_NO_PIPELINE):
+        b = sb.Engine(model, prior, flags=flags, **kw)
+        for j in range(model.n_stats):
+            b.set_ecdf(j, src.get_ecdf(j))
+        bufs = [th.copy(order="F"), u.copy(order="F"), rho.copy(order="F"), eps.copy(), cnt.copy()]
+        b.update_host(*bufs, n_upd * N)
+        assert b.timing()["host_ms"] > 0
+        outs.append(bufs)
+        dev = b.get_population()
+        for x, y in zip(dev, bufs[:3]):
+            assert np.array_equal(x, y)                     # what came home is what the device holds
+    for x, y in zip(outs[0], outs[1]):
+        assert np.array_equal(x, y)
+    for x, y in zip(orc.get_population(), outs[0][:3]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(orc.get_state()[0], outs[0][3]) and np.array_equal(orc.get_state()[1], outs[0][4])
+
+
 def test_negative_distance_is_an_error(gpu):
     """:185 -- a model returning negative prior distances aborts initialization (obs far below gives |.| >= 0, so use the
     second statistic of gauss_sample with a NaN-free negative trick: obs2 = -inf makes |obs2 - x| = inf, not negative; the
