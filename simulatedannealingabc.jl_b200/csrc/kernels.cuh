@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, cons
 }
 
 template <class M>
-__global__ void __launch_bounds__(CHUNK) simulate_accept_kernel(const UpdateArgs a, const SplitScratch w) {
+__global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kernel(const UpdateArgs a, const SplitScratch w) {
     constexpr int D = M::D, S = M::S;
     extern __shared__ double s_top[];
     stage_ecdf_top(a.ecdf, S, s_top);
@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(CHUNK) simulate_accept_kernel(const UpdateArgs
         q0 = __shfl_sync(0xffffffffu, q0, 0);
         if (q0 >= n_items) break;
         const unsigned q = q0 + lane;
+        const unsigned live = __ballot_sync(0xffffffffu, q < n_items);
         if (q < n_items) {
             const int64_t gi = a.act_off + (int64_t)w.idx[q];
             const uint32_t pid = a.particle_base + (uint32_t)gi;
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(CHUNK) simulate_accept_kernel(const UpdateArgs
 #pragma unroll
             for (int c = 0; c < D; ++c) thp[c] = w.theta[c * w.cap + q];
             Stream st(a.seed, pid, sweep, KIND_MODEL);
+            st.warp_mask = live;
             M::sim(thp, a.mp, st, rp);                                  // :315
             double Ssum = 0.0;
 #pragma unroll

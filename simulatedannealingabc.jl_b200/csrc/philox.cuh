@@ -47,9 +47,10 @@ SABC_HD U64x2 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
 // A stream = (seed, particle, sweep, kind); block j of it is one Philox call.
 struct Stream {
     uint32_t k0, k1, particle, sweep_lo, tag, next;
+    uint32_t warp_mask;   // lanes known to call the model together (0: the model asks __activemask())
     SABC_HD Stream(uint64_t seed, uint32_t particle_, uint64_t sweep, uint32_t kind)
         : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), particle(particle_), sweep_lo((uint32_t)sweep),
-          tag(kind | ((uint32_t)(sweep >> 32) << 4)), next(0) {}
+          tag(kind | ((uint32_t)(sweep >> 32) << 4)), next(0), warp_mask(0) {}
     SABC_HD U64x2 block(uint32_t j) const { return philox4x32_10(particle, sweep_lo, j, tag, k0, k1); }
     SABC_HD U64x2 draw() { return block(next++); }
 };

@@ -194,6 +194,7 @@ struct ModelPar { double v[MAX_MODEL_PAR]; };
 // C1/C5: 1-D Gaussian mean, sufficient-statistic form.  par: ybar_obs, sd_mean (= sigma/sqrt(n))
 struct GaussMean {
     static constexpr int D = 1, S = 1;
+    static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
     SABC_HD static void sim(const double (&th)[1], const ModelPar& mp, Stream& st, double (&rho)[1]) {
         double z0, z1; normal_pair(st.draw(), z0, z1);
         const double ysim = th[0] + mp.v[1] * z0;
@@ -206,6 +207,7 @@ struct GaussMean {
 template <int D_, int S_>
 struct GaussSample {
     static constexpr int D = D_, S = S_;
+    static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
     SABC_HD static void sim(const double (&th)[D_], const ModelPar& mp, Stream& st, double (&rho)[S_]) {
         const int n = (int)mp.v[0];
         const double sig = D_ >= 2 ? th[D_ - 1] : mp.v[1];
@@ -224,6 +226,7 @@ struct GaussSample {
 // C3: stochastic logistic growth, θ = (r, K, σ), T = 20 points.  par: x0, T, obs[T]
 struct Logistic {
     static constexpr int D = 3, S = 20;
+    static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
     SABC_HD static void sim(const double (&th)[3], const ModelPar& mp, Stream& st, double (&rho)[20]) {
         double x = mp.v[0];
 #pragma unroll
@@ -244,6 +247,7 @@ struct Logistic {
 // C4: SIR tau-leap, θ = (β, γ, ι, φ).  par: pop, T, tau, obs_total, obs_peak, obs_tpeak
 struct SirTauLeap {
     static constexpr int D = 4, S = 3;
+    static constexpr int SIM_MIN_BLOCKS = 4;   // cap at 64 registers: 32 warps per SM hide the FP64 latencies
     // Per step: n_inf ~ Poisson(β S I/pop τ) ∧ S, n_rec ~ Poisson(γ I τ) ∧ I, cases ~ Poisson(φ n_inf).  Written as a
     // per-lane state machine over sampler ATTEMPTS (phase 0/1/2 = the three draws of a step): every loop trip each
     // lane makes one attempt on its own current draw, so a PTRS rejection costs that lane one trip instead of
@@ -260,9 +264,8 @@ struct SirTauLeap {
         int64_t total = 0, peak = -1, tpeak = 0, ninf = 0;
         int t = 1, phase = 0;
         double lam = (((th[0] * (double)Sc) * (double)I) * inv_pop) * tau;
-        while (t <= T) {
-            int64_t k;
-            if (!poisson_attempt(lam, st, k)) continue;
+        // one accepted draw k moves the particle to its next draw
+        auto advance = [&](int64_t k) {
             if (phase == 0) {
                 ninf = k > Sc ? Sc : k;
                 lam = (th[1] * (double)I) * tau;
@@ -278,6 +281,14 @@ struct SirTauLeap {
                 lam = (((th[0] * (double)Sc) * (double)I) * inv_pop) * tau;
                 phase = 0; t++;
             }
+        };
+        // Every loop trip each lane makes ONE sampler attempt on its own current draw, so a PTRS rejection costs that lane
+        // one trip instead of stalling its warp.  (Parking the lanes that need the exact PTRS test or the inversion loop
+        // until enough of them wait was measured and is slower: the cheap part of a trip is not cheap enough, r1 notes.)
+        while (t <= T) {
+            int64_t k;
+            if (!poisson_attempt(lam, st, k)) continue;
+            advance(k);
         }
         const double d0 = (double)total - mp.v[3], d1 = (double)peak - mp.v[4], d2 = (double)tpeak - mp.v[5];
         rho[0] = d0 * d0; rho[1] = d1 * d1; rho[2] = d2 * d2;
