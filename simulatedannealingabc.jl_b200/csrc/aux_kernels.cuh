@@ -126,8 +126,8 @@ static __global__ void k_force_flag(DevState* ds, int flag) { ds->resample_flag 
 static __global__ void k_set_counters(DevState* ds, long long n_accept, long long n_resampling) {
     ds->n_accept = n_accept; ds->n_resampling = n_resampling;
 }
-static __global__ void k_recompute_lp(PopView pop, int64_t n, int D, const PriorSpec prior) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+static __global__ void k_recompute_lp(PopView pop, int64_t r0, int64_t r1, int D, const PriorSpec prior) {
+    for (int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (int64_t)gridDim.x * blockDim.x) {
         double lp = 0.0;
         for (int c = 0; c < D; ++c) {
             const double x = pop.theta[c * pop.ld + i];
@@ -377,7 +377,7 @@ static __global__ void k_finish(const FinishArgs a) {
         for (int j = 0; j < a.S; ++j) { ds->u_hi[j] = 0ull; ds->u_lo[j] = 0ull; }
         ds->n_acc_iter = 0ull;
         ds->resample_flag = 0;
-        ds->list_count[0] = ds->list_count[1] = ds->list_cursor[0] = ds->list_cursor[1] = 0u;
+        for (int k = 0; k < MAX_SLOTS; ++k) { ds->list_count[k] = 0u; ds->list_cursor[k] = 0u; }
         ds->t += 1; ds->ix += 1;
     }
 }
@@ -424,7 +424,7 @@ static __global__ void k_begin(DevState* ds, long long t, long long n_pop, long 
     ds->t = t; ds->ix = 1; ds->n_pop = n_pop; ds->checkpoint = checkpoint; ds->rec = 0; ds->last_cp = 0;
     for (int j = 0; j < MAX_S; ++j) { ds->u_hi[j] = 0ull; ds->u_lo[j] = 0ull; }
     ds->n_acc_iter = 0ull; ds->resample_flag = 0;
-    ds->list_count[0] = ds->list_count[1] = ds->list_cursor[0] = ds->list_cursor[1] = 0u;
+    for (int k = 0; k < MAX_SLOTS; ++k) { ds->list_count[k] = 0u; ds->list_cursor[k] = 0u; }
 }
 // Σu limbs of an existing u array (set_population, multi-GPU resampling)
 static __global__ void __launch_bounds__(CHUNK) k_sum_u(const double* u, int64_t ld, int64_t n, int S, unsigned long long* hi_out,

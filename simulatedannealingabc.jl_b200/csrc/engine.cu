@@ -98,10 +98,11 @@ struct sabc_engine {
     int grid_simacc = 0, bps_simacc = 0;
 
     // per-call hooks of the sweeps: kernel timing events and the copy/compute pipeline of the host-buffer call
-    std::vector<cudaEvent_t>* kev = nullptr;           // event pairs around the dominant kernel of each half
-    cudaEvent_t pipe_wait_half1 = nullptr;             // second half-sweep waits for the rest of the upload
-    cudaEvent_t pipe_rec_half0 = nullptr;              // recorded after the first half-sweep (early download of half 0)
-    std::function<int()> pipe_on_half0;                // enqueues that download once the event is in the stream
+    std::vector<cudaEvent_t>* kev = nullptr;           // event pairs around the dominant kernel of each (sub-)sweep
+    int pipe_nsub = 1;                                 // sub-ranges per half-sweep (1 = plain half-sweeps)
+    bool pipe_first = false, pipe_last = false;        // this update is the first / last one of a pipelined host call
+    std::function<int(int, int)> pipe_before;          // (half, sub): stream waits for the rows' upload, log-prior of the rows
+    std::function<int(int, int)> pipe_after;           // (half, sub): rows are final, enqueue their download
     cudaStream_t s_in = nullptr, s_out = nullptr;
     int64_t part_ld = 0, scratch_ld = 0, hist_cap = 0;
     int grid_update = 0, grid_aux = 0, bps_update = 0;
@@ -210,22 +211,13 @@ static int ecdf_build_column(sabc_engine* e, int j, const double* d_col, int64_t
     return ecdf_attach(e, j, knots, (int64_t)n_pos + 2, top_max_for(e->S));
 }
 
-static int launch_update_half(sabc_engine* e, int half) {
-    UpdateArgs a{};
-    a.pop = e->pop;
-    halves(e, half, a.act_off, a.act_n, a.ina_off, a.ina_n);
-    a.particle_base = (uint32_t)e->offset;
-    a.half = half; a.seed = e->seed; a.ds = e->b_ds.p; a.ecdf = e->b_ecdf.p;
-    a.rho_part = e->b_rho_part.p + (int64_t)half * e->S * e->part_ld;
-    a.part_ld = e->part_ld; a.n_eps = e->n_eps; a.top_doubles = e->top_doubles;
-    a.prop0 = e->prop_par[0]; a.prop1 = e->prop_par[1];
-    a.prior = e->prior; a.mp = e->mp;
-    if (a.act_n <= 0) return 0;
-    SABC_CUDA(e->model->launch_update(e->proposal, a, e->grid_update, e->smem_update, e->stream));
-    return 0;
+// rows [r0, r1) (relative to the half start) of sub-range `sub` of `nsub`; boundaries are multiples of the 256-group
+static void sub_range(int64_t act_n, int sub, int nsub, int64_t& r0, int64_t& r1) {
+    const int64_t per = (((act_n + nsub - 1) / nsub + CHUNK - 1) / CHUNK) * CHUNK;
+    r0 = std::min<int64_t>(act_n, (int64_t)sub * per);
+    r1 = std::min<int64_t>(act_n, r0 + per);
 }
-
-static UpdateArgs make_update_args(sabc_engine* e, int half) {
+static UpdateArgs make_update_args(sabc_engine* e, int half, int sub = 0, int nsub = 1) {
     UpdateArgs a{};
     a.pop = e->pop;
     halves(e, half, a.act_off, a.act_n, a.ina_off, a.ina_n);
@@ -235,6 +227,12 @@ static UpdateArgs make_update_args(sabc_engine* e, int half) {
     a.part_ld = e->part_ld; a.n_eps = e->n_eps; a.top_doubles = e->top_doubles;
     a.prop0 = e->prop_par[0]; a.prop1 = e->prop_par[1];
     a.prior = e->prior; a.mp = e->mp;
+    a.slot = half * MAX_SUB + sub;
+    if (nsub > 1) {
+        int64_t r0, r1;
+        sub_range(a.act_n, sub, nsub, r0, r1);
+        a.act_off += r0; a.act_n = r1 - r0; a.rho_part += r0 / CHUNK;
+    }
     return a;
 }
 static SplitScratch make_split(sabc_engine* e) {
@@ -244,16 +242,22 @@ static SplitScratch make_split(sabc_engine* e) {
     w.cap = e->n_local - e->n_local / 2;
     return w;
 }
-// split path, one half: propose + compact, then one simulation per lane over the work list
-static int launch_split_propose(sabc_engine* e, int half) {
-    const UpdateArgs a = make_update_args(e, half);
+static int launch_update_half(sabc_engine* e, int half, int sub = 0, int nsub = 1) {
+    const UpdateArgs a = make_update_args(e, half, sub, nsub);
+    if (a.act_n <= 0) return 0;
+    SABC_CUDA(e->model->launch_update(e->proposal, a, e->grid_update, e->smem_update, e->stream));
+    return 0;
+}
+// split path, one (sub-range of a) half: propose + compact, then one simulation per lane over the work list
+static int launch_split_propose(sabc_engine* e, int half, int sub = 0, int nsub = 1) {
+    const UpdateArgs a = make_update_args(e, half, sub, nsub);
     if (a.act_n <= 0) return 0;
     const int64_t groups = (a.act_n + CHUNK - 1) / CHUNK;
     SABC_CUDA(e->model->launch_propose(e->proposal, a, make_split(e), (int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), e->stream));
     return 0;
 }
-static int launch_split_simacc(sabc_engine* e, int half) {
-    const UpdateArgs a = make_update_args(e, half);
+static int launch_split_simacc(sabc_engine* e, int half, int sub = 0, int nsub = 1) {
+    const UpdateArgs a = make_update_args(e, half, sub, nsub);
     if (a.act_n <= 0) return 0;
     SABC_CUDA(e->model->launch_simacc(a, make_split(e), e->grid_simacc, e->smem_update, e->stream));
     return 0;
@@ -328,21 +332,22 @@ static int launch_finish(sabc_engine* e) {
 
 static int kernels_per_iteration(const sabc_engine* e) { return (e->split ? 6 : 2) + 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1; }
 
-// the two half-sweeps (:304-332) in the fused or the split form, with the optional per-call hooks
+// the two half-sweeps (:304-332) in the fused or the split form.  A pipelined host call cuts each half into sub-ranges
+// (identical results: the particles of a half-sweep are independent) so that transfers overlap at a finer grain.
 static int enqueue_sweeps(sabc_engine* e) {
+    const int nsub = e->pipe_nsub;
     for (int half = 0; half < 2; ++half) {
-        if (half == 1 && e->pipe_wait_half1) SABC_CUDA(cudaStreamWaitEvent(e->stream, e->pipe_wait_half1, 0));
-        if (e->split) SABC_TRY(launch_split_propose(e, half));
-        cudaEvent_t a = nullptr, b = nullptr;
-        if (e->kev) {
-            SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b));
-            SABC_CUDA(cudaEventRecord(a, e->stream));
-        }
-        if (e->split) SABC_TRY(launch_split_simacc(e, half)); else SABC_TRY(launch_update_half(e, half));
-        if (e->kev) { SABC_CUDA(cudaEventRecord(b, e->stream)); e->kev->push_back(a); e->kev->push_back(b); }
-        if (half == 0 && e->pipe_rec_half0) {
-            SABC_CUDA(cudaEventRecord(e->pipe_rec_half0, e->stream));
-            if (e->pipe_on_half0) SABC_TRY(e->pipe_on_half0());
+        for (int sub = 0; sub < nsub; ++sub) {
+            if (e->pipe_first && e->pipe_before) SABC_TRY(e->pipe_before(half, sub));
+            if (e->split) SABC_TRY(launch_split_propose(e, half, sub, nsub));
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (e->kev) {
+                SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b));
+                SABC_CUDA(cudaEventRecord(a, e->stream));
+            }
+            if (e->split) SABC_TRY(launch_split_simacc(e, half, sub, nsub)); else SABC_TRY(launch_update_half(e, half, sub, nsub));
+            if (e->kev) { SABC_CUDA(cudaEventRecord(b, e->stream)); e->kev->push_back(a); e->kev->push_back(b); }
+            if (e->pipe_last && e->pipe_after) SABC_TRY(e->pipe_after(half, sub));
         }
     }
     return e->split ? launch_split_stats(e) : 0;
@@ -663,27 +668,24 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
     std::vector<cudaEvent_t> kev;
     const bool time_kernels = (e->flags & SABC_FLAG_TIME_KERNELS) != 0;
     int rc = 0;
-    cudaEvent_t pipe_rec_pending = e->pipe_rec_half0;
-    const bool piped = e->pipe_wait_half1 || e->pipe_rec_half0;
+    const bool piped = (bool)e->pipe_before || (bool)e->pipe_after;
     if (e->world > 1) {
         SABC_CUDA(cudaEventRecord(ev0, e->stream));
         if (time_kernels) e->kev = &kev;
         for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) {
-            if (ix == 1) e->pipe_wait_half1 = nullptr;
-            e->pipe_rec_half0 = (ix == n_pop - 1) ? pipe_rec_pending : nullptr;
+            e->pipe_first = piped && ix == 0; e->pipe_last = piped && ix == n_pop - 1;
             rc = mg_iteration(e);
         }
-        e->kev = nullptr; e->pipe_wait_half1 = nullptr; e->pipe_rec_half0 = nullptr;
+        e->kev = nullptr; e->pipe_first = e->pipe_last = false;
         SABC_CUDA(cudaEventRecord(ev1, e->stream));
     } else if ((e->flags & SABC_FLAG_NO_GRAPH) || piped) {
         SABC_CUDA(cudaEventRecord(ev0, e->stream));
         if (time_kernels) e->kev = &kev;
         for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) {
-            if (ix == 1) e->pipe_wait_half1 = nullptr;                                  // upload overlap: first update only
-            e->pipe_rec_half0 = (ix == n_pop - 1) ? pipe_rec_pending : nullptr;         // early download: last update only
+            e->pipe_first = piped && ix == 0; e->pipe_last = piped && ix == n_pop - 1;   // upload overlap / early download
             rc = enqueue_iteration(e);
         }
-        e->kev = nullptr; e->pipe_wait_half1 = nullptr; e->pipe_rec_half0 = nullptr;
+        e->kev = nullptr; e->pipe_first = e->pipe_last = false;
         SABC_CUDA(cudaEventRecord(ev1, e->stream));
     } else {
         if (!e->graph_exec) {
@@ -707,8 +709,8 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     e->timing.update_ms = ms;
-    e->timing.kernel_launches = 2 * n_pop;
-    e->timing.total_launches = (int64_t)kernels_per_iteration(e) * n_pop;
+    e->timing.kernel_launches = 2 * n_pop * e->pipe_nsub;
+    e->timing.total_launches = ((int64_t)kernels_per_iteration(e) + (int64_t)(e->split ? 4 : 2) * (e->pipe_nsub - 1)) * n_pop;
     for (size_t k = 0; k + 1 < kev.size(); k += 2) {
         float t = 0.f; cudaEventElapsedTime(&t, kev[k], kev[k + 1]); e->timing.kernel_ms += t;
         cudaEventDestroy(kev[k]); cudaEventDestroy(kev[k + 1]);
@@ -742,7 +744,7 @@ int sabc_set_population(sabc_engine* e, const double* theta, const double* u, co
     SABC_CUDA(cudaMemcpyAsync(e->pop.theta, theta, n * e->D * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     SABC_CUDA(cudaMemcpyAsync(e->pop.u, u, n * e->S * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     SABC_CUDA(cudaMemcpyAsync(e->pop.rho, rho, n * e->S * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, (int64_t)n, e->D, e->prior);
+    k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, 0, (int64_t)n, e->D, e->prior);
     for (int k = 0; k < e->n_eps; ++k) e->eps[k] = eps[k];
     e->n_simulation = counters[0]; e->n_accept = counters[1]; e->n_resampling = counters[2]; e->n_population_updates = counters[3];
     SABC_CUDA(cudaMemcpyAsync(&e->b_ds.p->eps[0], e->eps, sizeof(double) * e->n_eps, cudaMemcpyHostToDevice, e->stream));
@@ -757,8 +759,9 @@ int sabc_set_population(sabc_engine* e, const double* theta, const double* u, co
 static int copy_rows(double* dst, const double* src, int64_t n, int ncol, int64_t r0, int64_t r1, cudaMemcpyKind kind, cudaStream_t st) {
     if (r1 <= r0) return 0;
     if (r0 == 0 && r1 == n) { SABC_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * ncol * sizeof(double), kind, st)); return 0; }
-    for (int c = 0; c < ncol; ++c)
-        SABC_CUDA(cudaMemcpyAsync(dst + (int64_t)c * n + r0, src + (int64_t)c * n + r0, (size_t)(r1 - r0) * sizeof(double), kind, st));
+    // one strided copy: ncol rows of (r1-r0) doubles, pitch = one column
+    SABC_CUDA(cudaMemcpy2DAsync(dst + r0, (size_t)n * sizeof(double), src + r0, (size_t)n * sizeof(double),
+                                (size_t)(r1 - r0) * sizeof(double), (size_t)ncol, kind, st));
     return 0;
 }
 
@@ -795,52 +798,78 @@ int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, doub
     }
     if (!e->s_in) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     if (!e->s_out) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-    cudaEvent_t evA, evB, evS0;
-    SABC_CUDA(cudaEventCreateWithFlags(&evA, cudaEventDisableTiming)); SABC_CUDA(cudaEventCreateWithFlags(&evB, cudaEventDisableTiming));
-    SABC_CUDA(cudaEventCreateWithFlags(&evS0, cudaEventDisableTiming));
-    auto cleanup2 = [&] { cudaEventDestroy(evA); cudaEventDestroy(evB); cudaEventDestroy(evS0); cleanup(); };
+    // 2 sub-ranges per half measured best on B200 (4.70 ms vs 4.85 at 1, 5.9 at 3, 6.8 at 4 per C4 step): the simulation
+    // kernel needs ~150 k items to fill the GPU, smaller sub-sweeps only add latency-bound tails.  SABC_PIPE_NSUB overrides.
+    const int nsub_env = getenv("SABC_PIPE_NSUB") ? atoi(getenv("SABC_PIPE_NSUB")) : 2;
+    const int nsub = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nsub_env, (int)MAX_SUB), h0 / 32768));
+    cudaEvent_t evT1, evUp[2][MAX_SUB], evDn[2][MAX_SUB];
+    std::vector<cudaEvent_t> evs;
+    auto mk = [&](cudaEvent_t& ev) { cudaError_t r = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); if (r == cudaSuccess) evs.push_back(ev); return r; };
+    auto cleanup2 = [&] { for (auto ev : evs) cudaEventDestroy(ev); cleanup(); };
+    SABC_CUDA(mk(evT1));
+    for (int h = 0; h < 2; ++h) for (int j = 0; j < nsub; ++j) { SABC_CUDA(mk(evUp[h][j])); SABC_CUDA(mk(evDn[h][j])); }
     const auto H2D = cudaMemcpyHostToDevice; const auto D2H = cudaMemcpyDeviceToHost;
-    // upload, part A (what the first half-sweep touches): theta, rows [0,h0) of u and rho
+    auto rows = [&](int half, int sub, int64_t& r0, int64_t& r1) {       // absolute row range of a sub-range
+        int64_t off, an, t0, t1;
+        halves(e, half, off, an, t0, t1);
+        sub_range(an, sub, nsub, r0, r1);
+        r0 += off; r1 += off;
+    };
+    // upload order = order of need: theta of the second half (partners of the first sweep), then per sub-range of the first
+    // half its rows of theta, u, rho; then the rows of u, rho of the second half
     SABC_CUDA(cudaEventRecord(a, e->s_in));
-    rc = copy_rows(e->pop.theta, theta, n, e->D, 0, n, H2D, e->s_in);
-    if (!rc) rc = copy_rows(e->pop.u, u, n, e->S, 0, h0, H2D, e->s_in);
-    if (!rc) rc = copy_rows(e->pop.rho, rho, n, e->S, 0, h0, H2D, e->s_in);
-    if (!rc) { SABC_CUDA(cudaEventRecord(evA, e->s_in)); }
-    // part B: the second half of u and rho, overlapping the first half-sweep
-    if (!rc) rc = copy_rows(e->pop.u, u, n, e->S, h0, n, H2D, e->s_in);
-    if (!rc) rc = copy_rows(e->pop.rho, rho, n, e->S, h0, n, H2D, e->s_in);
-    if (rc) { cleanup2(); return rc; }
-    SABC_CUDA(cudaEventRecord(evB, e->s_in));
+    rc = copy_rows(e->pop.theta, theta, n, e->D, h0, n, H2D, e->s_in);
+    if (!rc) { SABC_CUDA(cudaEventRecord(evT1, e->s_in)); }
+    for (int half = 0; half < 2 && !rc; ++half)
+        for (int j = 0; j < nsub && !rc; ++j) {
+            int64_t r0, r1; rows(half, j, r0, r1);
+            if (half == 0) rc = copy_rows(e->pop.theta, theta, n, e->D, r0, r1, H2D, e->s_in);
+            if (!rc) rc = copy_rows(e->pop.u, u, n, e->S, r0, r1, H2D, e->s_in);
+            if (!rc) rc = copy_rows(e->pop.rho, rho, n, e->S, r0, r1, H2D, e->s_in);
+            if (!rc) { SABC_CUDA(cudaEventRecord(evUp[half][j], e->s_in)); }
+        }
+    if (rc) { cudaStreamSynchronize(e->s_in); cleanup2(); return rc; }
     SABC_CUDA(cudaEventRecord(b, e->s_in));
-    // state scalars + cached log-prior once theta is there
-    SABC_CUDA(cudaStreamWaitEvent(e->stream, evA, 0));
-    k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, n, e->D, e->prior);
+    // state scalars; cached log-prior of the second half as soon as its theta is there
+    SABC_CUDA(cudaStreamWaitEvent(e->stream, evT1, 0));
+    k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, h0, n, e->D, e->prior);
     for (int k = 0; k < e->n_eps; ++k) e->eps[k] = eps[k];
     e->n_simulation = counters[0]; e->n_accept = counters[1]; e->n_resampling = counters[2]; e->n_population_updates = counters[3];
     SABC_CUDA(cudaMemcpyAsync(&e->b_ds.p->eps[0], e->eps, sizeof(double) * e->n_eps, H2D, e->stream));
     k_set_counters<<<1, 1, 0, e->stream>>>(e->b_ds.p, e->n_accept, e->n_resampling);
     SABC_CUDA(cudaGetLastError());
+    if (e->proposal == PROP_RW)        // update_proposal! (:284) reads the whole population before the first sweep
+        SABC_CUDA(cudaStreamWaitEvent(e->stream, evUp[0][nsub - 1], 0));
     e->initialised = true;
     const int64_t n_res_before = e->n_resampling;
-    // hooks: second half-sweep of the first update waits for part B; after the first half-sweep of the last update
-    // rows [0,h0) are final (unless a resampling follows) and go home while the second half-sweep runs
-    e->pipe_wait_half1 = evB;
-    e->pipe_rec_half0 = evS0;
-    e->pipe_on_half0 = [&]() -> int {
-        SABC_CUDA(cudaStreamWaitEvent(e->s_out, evS0, 0));
-        SABC_TRY(copy_rows(theta, e->pop.theta, n, e->D, 0, h0, D2H, e->s_out));
-        SABC_TRY(copy_rows(u, e->pop.u, n, e->S, 0, h0, D2H, e->s_out));
-        return copy_rows(rho, e->pop.rho, n, e->S, 0, h0, D2H, e->s_out);
+    e->pipe_nsub = nsub;
+    e->pipe_before = [&](int half, int sub) -> int {
+        SABC_CUDA(cudaStreamWaitEvent(e->stream, evUp[half][sub], 0));
+        if (half == 0) {
+            int64_t r0, r1; rows(half, sub, r0, r1);
+            if (r1 > r0) k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, r0, r1, e->D, e->prior);
+        }
+        return 0;
+    };
+    // after its (sub-)sweep of the last update a row range is final (unless a resampling follows): it goes home while
+    // the next sub-ranges are being simulated
+    e->pipe_after = [&](int half, int sub) -> int {
+        int64_t r0, r1; rows(half, sub, r0, r1);
+        SABC_CUDA(cudaEventRecord(evDn[half][sub], e->stream));
+        SABC_CUDA(cudaStreamWaitEvent(e->s_out, evDn[half][sub], 0));
+        SABC_TRY(copy_rows(theta, e->pop.theta, n, e->D, r0, r1, D2H, e->s_out));
+        SABC_TRY(copy_rows(u, e->pop.u, n, e->S, r0, r1, D2H, e->s_out));
+        return copy_rows(rho, e->pop.rho, n, e->S, r0, r1, D2H, e->s_out);
     };
     rc = sabc_update(e, n_simulation, checkpoint_history);          // blocks until the updates are done
-    e->pipe_wait_half1 = nullptr; e->pipe_rec_half0 = nullptr; e->pipe_on_half0 = nullptr;
+    e->pipe_before = nullptr; e->pipe_after = nullptr; e->pipe_nsub = 1;
     const sabc_timing t_upd = e->timing;
     if (!rc) {
         SABC_CUDA(cudaEventRecord(c, e->s_out));
-        const bool resampled = e->n_resampling != n_res_before;     // theta, u of every row changed: fetch them again
-        rc = copy_rows(theta, e->pop.theta, n, e->D, resampled ? 0 : h0, n, D2H, e->s_out);
-        if (!rc) rc = copy_rows(u, e->pop.u, n, e->S, resampled ? 0 : h0, n, D2H, e->s_out);
-        if (!rc) rc = copy_rows(rho, e->pop.rho, n, e->S, h0, n, D2H, e->s_out);
+        if (e->n_resampling != n_res_before) {                      // theta, u of every row changed after the sweeps
+            rc = copy_rows(theta, e->pop.theta, n, e->D, 0, n, D2H, e->s_out);
+            if (!rc) rc = copy_rows(u, e->pop.u, n, e->S, 0, n, D2H, e->s_out);
+        }
         if (!rc) rc = sabc_get_state(e, eps, counters);
     }
     if (!rc) {

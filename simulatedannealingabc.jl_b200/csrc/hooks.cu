@@ -273,7 +273,7 @@ int sabc_prior_logpdf(int32_t d, const int32_t* kind, const double* par, const d
     DevBuf<double> th, lp;
     SABC_TRY(upload(th, theta, (size_t)n * d)); SABC_CUDA(lp.alloc((size_t)n));
     PopView pop{th.p, nullptr, nullptr, lp.p, n};
-    k_recompute_lp<<<grid_for(n), 256>>>(pop, n, d, p);
+    k_recompute_lp<<<grid_for(n), 256>>>(pop, 0, n, d, p);
     SABC_CUDA(cudaGetLastError());
     return download(lp_out, lp, (size_t)n);
 }

@@ -13,6 +13,9 @@ namespace sabc {
 
 // Device-resident algorithm state: everything that changes between population updates lives
 // here, so one captured CUDA graph can be replayed for every iteration without host round trips.
+constexpr int MAX_SUB = 8;                 // sub-ranges of a half-sweep (transfer pipelining of the host-buffer call)
+constexpr int MAX_SLOTS = 2 * MAX_SUB;
+
 struct DevState {
     // [u_hi, u_lo, n_acc_iter] and [r_hi, r_lo] are contiguous: each is one integer all-reduce on multi-GPU
     unsigned long long u_hi[MAX_S], u_lo[MAX_S];   // exact Σu limbs of the running iteration
@@ -28,7 +31,7 @@ struct DevState {
     long long ix, n_pop, checkpoint, rec, last_cp; // position inside the current update() call
     long long n_accept, n_resampling;
     int resample_flag, error_flag;
-    unsigned int list_count[2], list_cursor[2];    // split path: work-list length and fetch cursor per half
+    unsigned int list_count[MAX_SLOTS], list_cursor[MAX_SLOTS];   // split path: work-list length / fetch cursor per (half, sub-range)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -163,6 +166,7 @@ struct UpdateArgs {
     uint32_t particle_base;                   // global index of local particle 0 (Philox counter)
     int32_t half;
     uint64_t seed;
+    int32_t slot;                             // work-list counter slot = half * MAX_SUB + sub-range
     DevState* ds;
     const EcdfStat* ecdf;                     // [S] descriptors in HBM
     double* rho_part;                         // [S][part_ld] per-group ρ sums of this half
@@ -181,8 +185,8 @@ struct SplitScratch {
     double* lp;               // [cap] logpdf(prior, θ′)
     double* lf;               // [cap] log_factor of the proposal
     uint32_t* idx;            // [cap] local index (within the active half) of the particle
-    unsigned int* count;      // [2] entries per half
-    unsigned int* cursor;     // [2] dynamic work cursor of the simulation kernel per half
+    unsigned int* count;      // [MAX_SLOTS] entries per (half, sub-range)
+    unsigned int* cursor;     // [MAX_SLOTS] dynamic work cursor of the simulation kernel
     int64_t cap;
 };
 
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, cons
         }
         const unsigned mask = __ballot_sync(0xffffffffu, ok);
         unsigned base = 0;
-        if (lane == 0 && mask) base = atomicAdd(&w.count[a.half], (unsigned)__popc(mask));
+        if (lane == 0 && mask) base = atomicAdd(&w.count[a.slot], (unsigned)__popc(mask));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (ok) {
             const int64_t q = base + __popc(mask & ((1u << lane) - 1u));
@@ -365,11 +369,11 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
 #pragma unroll
     for (int j = 0; j < S; ++j) eps[j] = a.ds->eps[a.n_eps == 1 ? 0 : j];
     const int64_t ld = a.pop.ld;
-    const unsigned n_items = w.count[a.half];
+    const unsigned n_items = w.count[a.slot];
     unsigned n_acc = 0;
     for (;;) {
         unsigned q0 = 0;
-        if (lane == 0) q0 = atomicAdd(&w.cursor[a.half], 32u);
+        if (lane == 0) q0 = atomicAdd(&w.cursor[a.slot], 32u);
         q0 = __shfl_sync(0xffffffffu, q0, 0);
         if (q0 >= n_items) break;
         const unsigned q = q0 + lane;
