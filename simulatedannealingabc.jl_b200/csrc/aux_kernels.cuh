@@ -28,9 +28,12 @@ static __global__ void k_ecdf_ends(double* knots, int64_t n_pos) {   // values =
     knots[0] = 0.0;
     knots[n_pos + 1] = knots[n_pos] * 1.5;
 }
-static __global__ void k_sample16(const double* in, int64_t cnt_out, double* out) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt_out; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = in[i * ECDF_FANOUT];
+static __global__ void k_sample16(const double* in, int64_t cnt_out, double* out) {   // out has cnt_out + ECDF_PAD entries
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt_out + ECDF_PAD; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = i < cnt_out ? in[i * ECDF_FANOUT] : dinf();
+}
+static __global__ void k_fill_inf(double* p, int n) {
+    if (threadIdx.x < n) p[threadIdx.x] = dinf();
 }
 
 // u = G(ρ) for every particle and statistic + exact Σu limbs

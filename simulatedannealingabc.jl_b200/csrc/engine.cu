@@ -152,8 +152,8 @@ static int ecdf_attach(sabc_engine* e, int j, DevBuf<double>* knots, int64_t L, 
         const int64_t cnt = (st.cnt[st.nlev - 1] + ECDF_FANOUT - 1) / ECDF_FANOUT;
         auto* b = new DevBuf<double>();
         e->ecdf_bufs.push_back(b);
-        SABC_CUDA(b->alloc((size_t)cnt));
-        const int grid = (int)std::min<int64_t>((cnt + 255) / 256, 4096);
+        SABC_CUDA(b->alloc((size_t)cnt + ECDF_PAD));
+        const int grid = (int)std::min<int64_t>((cnt + ECDF_PAD + 255) / 256, 4096);
         k_sample16<<<grid, 256, 0, e->stream>>>(st.lev[st.nlev - 1], cnt, b->p);
         SABC_CUDA(cudaGetLastError());
         st.lev[st.nlev] = b->p; st.cnt[st.nlev] = cnt; st.nlev++;
@@ -197,7 +197,8 @@ static int ecdf_build_column(sabc_engine* e, int j, const double* d_col, int64_t
     SABC_CUDA(cudaGetLastError());
     auto* knots = new DevBuf<double>();
     e->ecdf_bufs.push_back(knots);
-    SABC_CUDA(knots->alloc((size_t)n + 2));
+    SABC_CUDA(knots->alloc((size_t)n + 2 + ECDF_PAD));
+    k_fill_inf<<<1, 32, 0, e->stream>>>(knots->p + n + 2, ECDF_PAD);   // entries L..n+1 are +inf sentinels of the sort already
     size_t tmp_bytes = 0;
     SABC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys.p, knots->p + 1, (int64_t)n, 0, 64, e->stream));
     SABC_CUDA(cub_tmp.ensure(tmp_bytes));
@@ -919,8 +920,9 @@ int sabc_set_ecdf(sabc_engine* e, int32_t stat, const double* knots, int64_t L) 
     SABC_CUDA(cudaSetDevice(e->device));
     auto* b = new DevBuf<double>();
     e->ecdf_bufs.push_back(b);
-    SABC_CUDA(b->alloc((size_t)L));
+    SABC_CUDA(b->alloc((size_t)L + ECDF_PAD));
     SABC_CUDA(cudaMemcpyAsync(b->p, knots, (size_t)L * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    k_fill_inf<<<1, 32, 0, e->stream>>>(b->p + L, ECDF_PAD);
     SABC_TRY(ecdf_attach(e, stat, b, L, top_max_for(e->S)));
     bool all = true;
     for (int j = 0; j < e->S; ++j) all = all && e->h_ecdf[j].L > 0;

@@ -107,8 +107,8 @@ struct HookEcdf {
             const int64_t cnt = (st.cnt[st.nlev - 1] + ECDF_FANOUT - 1) / ECDF_FANOUT;
             auto* b = new DevBuf<double>();
             levels.push_back(b);
-            SABC_CUDA(b->alloc((size_t)cnt));
-            k_sample16<<<grid_for(cnt), 256>>>(st.lev[st.nlev - 1], cnt, b->p);
+            SABC_CUDA(b->alloc((size_t)cnt + ECDF_PAD));
+            k_sample16<<<grid_for(cnt + ECDF_PAD), 256>>>(st.lev[st.nlev - 1], cnt, b->p);
             SABC_CUDA(cudaGetLastError());
             st.lev[st.nlev] = b->p; st.cnt[st.nlev] = cnt; st.nlev++;
         }
@@ -174,7 +174,10 @@ int sabc_ecdf_build(const double* dist, int64_t n, double* knots_out, int64_t* L
 int sabc_ecdf_transform(const double* knots, int64_t L, const double* rho, int64_t m, double* u_out) {
     if (!knots || !rho || !u_out || L < 3) return set_error(SABC_ERR_INVALID, "bad argument");
     DevBuf<double> dk, dr, du;
-    SABC_TRY(upload(dk, knots, (size_t)L)); SABC_TRY(upload(dr, rho, (size_t)m)); SABC_CUDA(du.alloc((size_t)m));
+    SABC_CUDA(dk.alloc((size_t)L + ECDF_PAD));
+    SABC_CUDA(cudaMemcpy(dk.p, knots, (size_t)L * sizeof(double), cudaMemcpyHostToDevice));
+    k_fill_inf<<<1, 32>>>(dk.p + L, ECDF_PAD);
+    SABC_TRY(upload(dr, rho, (size_t)m)); SABC_CUDA(du.alloc((size_t)m));
     HookEcdf h;
     SABC_TRY(h.attach(dk.p, L, 2048));
     const size_t smem = (size_t)h.st.cnt[h.st.nlev - 1] * sizeof(double);

@@ -17,6 +17,7 @@ constexpr int MAX_S = 32;           // max summary statistics
 constexpr int MAX_MODEL_PAR = 40;   // doubles in a model parameter blob
 constexpr int ECDF_MAX_LEVELS = 8;
 constexpr int ECDF_FANOUT = 16;     // one 128-byte line of knots per index node
+constexpr int ECDF_PAD = 16;        // +inf entries appended to every level (whole-node loads never leave the buffer)
 constexpr int CHUNK = 256;          // particles per tree-sum group == threads per CTA
 
 enum Algorithm : int32_t { ALG_SINGLE_EPS = 0, ALG_MULTI_EPS = 1 };
@@ -151,15 +152,42 @@ SABC_HD int64_t count_less(const double* a, int64_t n, double x) {
     return lo;
 }
 
+#if defined(__CUDACC__)
+// same count over an array staged in shared memory, 8-ary: each round reads 7 pivots at once, so a 2048-entry level
+// costs 4 dependent shared-memory latencies instead of 11
+SABC_D int count_less_smem(const double* a, int n, double x) {
+    int lo = 0, len = n;
+    while (len > 0) {
+        const int step = (len + 7) >> 3;
+        int m = 0;
+#pragma unroll
+        for (int i = 1; i <= 7; ++i) {
+            const int q = i * step - 1;
+            m += (q < len && a[lo + q] < x) ? 1 : 0;       // pivots are sorted: the true ones form a prefix
+        }
+        lo += m * step;
+        len = (m == 7) ? len - 7 * step : (step - 1 < len - m * step ? step - 1 : len - m * step);
+    }
+    return lo;
+}
+// one 16-entry index node (an aligned 128-byte line, levels are padded with +inf): branch-free binary search, 5 probes.
+// Fetching the whole line at once (8 x 16 B, one latency) was measured 1.7x SLOWER on C5: the kernel is bound by
+// L1/LSU wavefronts of scattered accesses (63 % of peak, profiles/r1_c5_update_half_v0_ncu.txt), not by the probe chain.
+SABC_D int count_less16(const double* node, double x) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 8; step >= 1; step >>= 1) lo += (__ldg(node + lo + step - 1) < x) ? step : 0;
+    return lo + ((__ldg(node + lo) < x) ? 1 : 0);
+}
+
 SABC_D double ecdf_eval(const EcdfStat& e, const double* s_top, double rho) {
     const double x = rho > e.kmax ? e.kmax : (rho < 0.0 ? 0.0 : rho);        // Flat(): clamp to [K_1, K_L]
     const int top = e.nlev - 1;
-    int64_t lb = count_less(s_top + e.top_off, e.cnt[top], x);              // searchsortedfirst on the top level
+    int64_t lb = count_less_smem(s_top + e.top_off, (int)e.cnt[top], x);    // searchsortedfirst on the top level
     for (int lv = top - 1; lv >= 0; --lv) {
         if (lb > 0) {
             const int64_t base = (lb - 1) * ECDF_FANOUT;
-            int64_t n = e.cnt[lv] - base; if (n > ECDF_FANOUT) n = ECDF_FANOUT;
-            lb = base + count_less(e.lev[lv] + base, n, x);
+            lb = base + (int64_t)count_less16(e.lev[lv] + base, x);
         }
     }
     int64_t j = lb > 0 ? lb - 1 : 0;                                          // k > 1 && (k -= 1)
@@ -171,6 +199,7 @@ SABC_D double ecdf_eval(const EcdfStat& e, const double* s_top, double rho) {
     const double m = (y1 - y0) / (kj1 - kj);
     return y0 + m * (x - kj);
 }
+#endif
 
 // host/CPU-free reference form used by the unit hook kernel (plain binary search over the knots)
 SABC_HD double ecdf_eval_flat(const double* K, int64_t L, double rho) {
