@@ -62,37 +62,53 @@ def algorithmic_bytes_per_update(d: int, s: int, accept_frac: float) -> float:
     return 8 * (d + s) + 8 + 16 * d + 32 * s + accept_frac * (8 * (d + 2 * s) + 8) + (1 - accept_frac) * 8 * s
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md): one streaming nvidia-smi process
+    sampling every 50 ms, started before and killed after the region."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.proc, self.samples = index, None, []
 
-    def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        self.samples = [[x.strip() for x in line.split(",")] for line in out.splitlines() if line.count(",") >= 6]
 
     def summary(self) -> dict:
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        rows = [(num(s[0]), num(s[1]), num(s[2]), s) for s in self.samples]
+        rows = [r for r in rows if r[0] is not None]
+        # "under load": power above the idle floor (the first sample is taken before the region starts)
+        pmax = max([r[2] for r in rows if r[2] is not None], default=0.0)
+        loaded = [r for r in rows if r[2] is not None and r[2] >= 0.5 * pmax] or rows
         reasons = set()
-        for s in self.samples:
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+        for r in loaded:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3][3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        return {"sm_mhz": statistics.median([r[0] for r in loaded]) if loaded else None,
+                "sm_max_mhz": max([r[1] for r in rows if r[1] is not None], default=None),
+                "power_w_max": pmax or None, "reasons": sorted(reasons), "samples": len(rows), "samples_under_load": len(loaded)}
 
 
 def measured_peak_hbm() -> tuple[float, str]:
@@ -126,12 +142,12 @@ def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, ste
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer (e2e) leg; default min(steps, 10)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer (e2e) leg; default min(steps, 50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay the CUDA graph in the timed region (kernel times then come from a separate pass)")
     args = ap.parse_args()
@@ -211,7 +227,7 @@ def main():
     barrier()
     t = eng.timing()
     if rank == 0:
-        sampler.stop_flag.set(); sampler.join(timeout=2)
+        sampler.stop()
     cnt1 = eng.get_state()[1]
     ms_total = max_over_ranks(t["update_ms"])
     value = args.steps * N / (ms_total * 1e-3)
@@ -232,10 +248,19 @@ def main():
     bytes_per_launch = bytes_per_update * (n_per_gpu / 2)
     achieved = bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_hbm()
+    traffic = None                         # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if model.name == "sir_tauleap" and n_per_gpu == 1_250_000:
+            traffic = tr.get("simulate_accept_kernel<sir_tauleap>")
+        elif model.name == "gauss_mean" and n_per_gpu == 10_000_000:
+            traffic = tr.get("update_half_kernel<gauss_mean, DE>@5000000")
+    except Exception:
+        pass
 
     # end-to-end through the host-buffer call (what Julia's update_population!(::SABCresult) would ccall): every step uploads
     # the slice (θ,u,ρ,ε,counters) from pinned memory, runs one population update and downloads the result
-    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    e2e_steps = args.e2e_steps or min(args.steps, 50)
     import ctypes as C
     nl = eng.n_local
     sizes = [nl * d, nl * s, nl * s]
@@ -282,7 +307,7 @@ def main():
                 "how": "sabc_update_host per step: pinned host (theta,u,rho,eps,counters) -> device, one population update, device -> host; "
                        "CUDA events from the first uploaded byte to the last downloaded byte, transfers pipelined with the half-sweeps"},
         "gpu_launches": int(t["total_launches"]),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": (f"simulate_accept_kernel<{model.name}> (split path: propose -> compacted simulate+accept -> stats)"
                                 if model.name in ("sir_tauleap", "logistic") else f"update_half_kernel<{model.name}, DE>"), "avg_kernel_ms": avg_kernel_ms, "kernel_launches": int(kernel_launches),
                      "kernel_share_of_step": kernel_ms / t["update_ms"] if time_kernels_live else None,
