@@ -130,6 +130,8 @@ def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, ste
     o.init(); o.update(n_cal); o.update(3 * n_cal)
     rate = 3 * n_cal / max(o.seconds, 1e-6)
     n = int(min(max_particles, max(n_cal, rate * target_seconds / max(steps + warmup, 1))))
+    if n == max_particles:                 # the full population already fits the time budget: spend the rest on more updates
+        steps = max(steps, min(int(rate * target_seconds / n) - warmup, 200))
     o = ob.OracleEngine(model, prior, n_particles=n, resample=2 * n, **kw)
     o.init()
     if warmup:
