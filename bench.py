@@ -118,7 +118,8 @@ def measured_peak_hbm() -> tuple[float, str]:
         return 6650.0, "B200_PROFILING.md fallback (of fallback)"
 
 
-def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, steps: int, warmup: int, max_particles: int):
+def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, steps: int, warmup: int, max_particles: int,
+                          fixed_steps: bool = True):
     """Time the oracle's update loop (C restatement of the reference, OpenMP over particles exactly where the reference
     uses Threads.@threads) on a bounded sample of the workload.  Returns (updates/s, cores, description, ms_per_step)."""
     import oracle_binding as ob
@@ -130,7 +131,7 @@ def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, ste
     o.init(); o.update(n_cal); o.update(3 * n_cal)
     rate = 3 * n_cal / max(o.seconds, 1e-6)
     n = int(min(max_particles, max(n_cal, rate * target_seconds / max(steps + warmup, 1))))
-    if n == max_particles:                 # the full population already fits the time budget: spend the rest on more updates
+    if n == max_particles and not fixed_steps:   # the full population already fits the time budget: spend the rest on more updates
         steps = max(steps, min(int(rate * target_seconds / n) - warmup, 200))
     o = ob.OracleEngine(model, prior, n_particles=n, resample=2 * n, **kw)
     o.init()
@@ -142,6 +143,13 @@ def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, ste
 
 
 def main():
+    # stdout carries exactly one JSON line: everything libraries print there (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -178,7 +186,7 @@ def main():
                                  "note": "C/OpenMP restatement of the reference (oracle/), not the Julia package: julia is not installed"},
                 "e2e": {"value": val, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -320,10 +328,10 @@ def main():
         "clocks": sampler.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, sample, _ = cpu_oracle_throughput(model, prior, algorithm, target_seconds=15.0, steps=3, warmup=1, max_particles=n_per_gpu)
+        val, cores, sample, _ = cpu_oracle_throughput(model, prior, algorithm, target_seconds=15.0, steps=3, warmup=1, max_particles=n_per_gpu, fixed_steps=False)
         line["cpu_baseline"] = {"value": val, "unit": "particle-updates/s", "cores": cores, "kind": "port", "sample": sample,
                                 "note": "C/OpenMP restatement of the reference (oracle/); julia is not installed"}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -548,6 +548,16 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
         int rc = e->comm.init(c->nccl_unique_id, e->rank, world);
         if (rc == 0) rc = mg_warm_p2p(e);
         if (rc) return fail(rc);
+        // work space of the global resampling, allocated once (a cudaMalloc inside the update loop costs tens of ms)
+        const size_t Ng = (size_t)e->N, Nt = (Ng + TILE - 1) / TILE;
+        cudaError_t ce2 = e->mg.F.alloc(Ng);
+        if (ce2 == cudaSuccess) ce2 = e->mg.src.alloc(Ng);
+        if (ce2 == cudaSuccess) ce2 = e->mg.tsum.alloc(Nt);
+        if (ce2 == cudaSuccess) ce2 = e->mg.toff.alloc(Nt);
+        if (ce2 == cudaSuccess) ce2 = e->mg.scalar.alloc(1);
+        if (ce2 == cudaSuccess) ce2 = e->mg.flag.alloc(1);
+        if (ce2 == cudaSuccess) ce2 = e->mg.sb.alloc((size_t)(e->D + e->S + 1) * (n + n / 4 + 4096));
+        if (ce2 != cudaSuccess) return fail(set_error(SABC_ERR_CUDA, "multi-GPU work space allocation failed: %s", cudaGetErrorString(ce2)));
     }
     *out = e;
     return 0;

@@ -38,7 +38,7 @@ for cfg in args.configs.split(","):
             t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         row = {"config": cfg, "n_particles": N, "n_gpus": world, "ms_per_update": ms / args.steps, "updates_per_s": args.steps * N / (ms * 1e-3)}
         if args.cpu and rank == 0:
-            val, cores, sample, _ = cpu_oracle_throughput(model, prior, alg, target_seconds=6.0, steps=3, warmup=1, max_particles=min(N, 2_000_000))
+            val, cores, sample, _ = cpu_oracle_throughput(model, prior, alg, target_seconds=6.0, steps=3, warmup=1, max_particles=min(N, 2_000_000), fixed_steps=False)
             row.update(cpu_updates_per_s=val, cpu_cores=cores, cpu_sample=sample)
         eng.close()
         if rank == 0:
