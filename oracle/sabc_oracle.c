@@ -559,6 +559,24 @@ static int model_sim(int32_t id, int32_t d, int32_t s, const double* mp, const d
         double d0 = (double)total - mp[3], d1 = (double)peak - mp[4], d2 = (double)tpeak - mp[5];
         rho[0] = d0 * d0; rho[1] = d1 * d1; rho[2] = d2 * d2;
         return 0; }
+    case ORC_MODEL_SIR_GILLESPIE: {     /* docs/src/example.md:75-122,143-147; par: S0, I0, R0, t_max, obs_total, obs_peak, obs_tpeak */
+        double S = mp[0], I = mp[1], R = mp[2], tmax = mp[3];
+        double Npop = (S + I) + R, t = 0.0, peak = I, tpeak = 0.0;
+        for (int ev = 0; ev < 65536 && t < tmax && I > 0.0; ++ev) {           /* while t < t_max && I > 0  (:91) */
+            double inf = ((th[0] * S) * I) / Npop;                               /* :93 */
+            double rec = th[1] * I;                                              /* :94 */
+            double tot = inf + rec;
+            stream_next(&st, &a, &b);
+            t = t + (-orc_log(u53_open0(a))) / tot;                              /* :98-99 rand(Exponential(1/total_rate)) */
+            if (u53(b) < inf / tot) { S -= 1.0; I += 1.0; }                      /* :102-105 */
+            else { I -= 1.0; R += 1.0; }                                         /* :107-109 */
+            if (I > peak) { peak = I; tpeak = t; }                               /* maximum(sim.I), sim.time[argmax(sim.I)] */
+        }
+        double d0 = R - mp[4], d1 = peak - mp[5], d2 = tpeak - mp[6];
+        d0 = d0 * d0; d1 = d1 * d1; d2 = d2 * d2;                                /* abs2 (:143-147) */
+        if (s >= 3) { rho[0] = d0; rho[1] = d1; rho[2] = d2; }
+        else rho[0] = (d0 + d1) + d2;                                            /* f_dist_single_stat = sum (:152) */
+        return 0; }
     default: return -1;
     }
 }

@@ -43,6 +43,8 @@ static void ensure_builtin_models() {
         r.push_back(ModelLaunchers<GaussSample<2, 2>>::vtable("gauss_sample_d2s2"));
         r.push_back(ModelLaunchers<Logistic>::vtable("logistic", 1));
         r.push_back(ModelLaunchers<SirTauLeap>::vtable("sir_tauleap", 1));
+        r.push_back(ModelLaunchers<SirGillespie<3>>::vtable("sir_gillespie_s3", 1));
+        r.push_back(ModelLaunchers<SirGillespie<1>>::vtable("sir_gillespie_s1", 1));
     });
 }
 const ModelVTable* find_model(const char* name) {

@@ -324,4 +324,31 @@ struct SirTauLeap {
     }
 };
 
+// The reference's documented example (docs/src/example.md:75-122): event-driven (Gillespie) SIR, θ = (β, γ), S0=99, I0=1,
+// t_max=160; statistics abs2 of total infected, peak infected, time of the peak (:143-147), or their sum (S_ == 1, :152).
+// par: S0, I0, R0, t_max, obs_total, obs_peak, obs_tpeak.  One Philox block per event: waiting time and event type.
+template <int S_>
+struct SirGillespie {
+    static constexpr int D = 2, S = S_;
+    static constexpr int SIM_MIN_BLOCKS = 4;
+    SABC_HD static void sim(const double (&th)[2], const ModelPar& mp, Stream& st, double (&rho)[S_]) {
+        double Sc = mp.v[0], I = mp.v[1], R = mp.v[2];
+        const double tmax = mp.v[3], Npop = (Sc + I) + R;
+        double t = 0.0, peak = I, tpeak = 0.0;
+        for (int ev = 0; ev < 65536 && t < tmax && I > 0.0; ++ev) {
+            const double inf = ((th[0] * Sc) * I) / Npop;
+            const double rec = th[1] * I;
+            const double tot = inf + rec;
+            const U64x2 w = st.draw();
+            t = t + (-det_log(u53_open0(w.a))) / tot;
+            if (u53(w.b) < inf / tot) { Sc -= 1.0; I += 1.0; } else { I -= 1.0; R += 1.0; }
+            if (I > peak) { peak = I; tpeak = t; }
+        }
+        double d0 = R - mp.v[4], d1 = peak - mp.v[5], d2 = tpeak - mp.v[6];
+        d0 = d0 * d0; d1 = d1 * d1; d2 = d2 * d2;
+        if (S_ >= 3) { rho[0] = d0; rho[S_ >= 3 ? 1 : 0] = d1; rho[S_ >= 3 ? 2 : 0] = d2; }
+        else rho[0] = (d0 + d1) + d2;
+    }
+};
+
 }  // namespace sabc

@@ -146,6 +146,10 @@ function update_population!(res::SABCresult, f_dist::DeviceModel, prior::Distrib
     res
 end
 
-export DeviceModel, gauss_mean, gauss_sample, logistic, sir_tauleap
+# the package's documented example (docs/src/example.md): event-driven SIR, f_dist_multi_stats / f_dist_single_stat
+sir_gillespie(obs_total, obs_peak, obs_tpeak; S0=99, I0=1, R0=0, t_max=160.0, single_stat=false) =
+    DeviceModel("sir_gillespie_s$(single_stat ? 1 : 3)", 2, single_stat ? 1 : 3, Float64[S0, I0, R0, t_max, obs_total, obs_peak, obs_tpeak])
+
+export DeviceModel, gauss_mean, gauss_sample, logistic, sir_tauleap, sir_gillespie
 
 end # module

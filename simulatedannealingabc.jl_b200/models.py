@@ -61,6 +61,14 @@ def sir_tauleap(obs_total: float, obs_peak: float, obs_tpeak: float, pop: float 
     return DeviceModel("sir_tauleap", 4, 3, np.array([pop, n_steps, tau, obs_total, obs_peak, obs_tpeak]))
 
 
+def sir_gillespie(obs_total: float, obs_peak: float, obs_tpeak: float, *, S0: int = 99, I0: int = 1, R0: int = 0,
+                  t_max: float = 160.0, single_stat: bool = False) -> DeviceModel:
+    """The reference's documented example (docs/src/example.md:75-152): event-driven SIR, θ = (β, γ); distances abs2 of total
+    infected, peak infected and time of the peak (`f_dist_multi_stats`), or their sum (`f_dist_single_stat`)."""
+    s = 1 if single_stat else 3
+    return DeviceModel(f"sir_gillespie_s{s}", 2, s, np.array([S0, I0, R0, t_max, obs_total, obs_peak, obs_tpeak], dtype=np.float64))
+
+
 def registered() -> list[str]:
     L = _lib.lib()
     return [L.sabc_model_name(i).decode() for i in range(L.sabc_model_count())]

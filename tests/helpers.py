@@ -27,6 +27,8 @@ def model_cases():
         "gauss_sample_d2s2": (m.gauss_sample(10, 2.0, 42.5, n_para=2, second_is_sum=True),
                               sb.product_distribution([sb.Normal(0, 2), sb.Uniform(0, 2)])),
         "logistic": (m.logistic(obs_logistic()), sb.product_distribution([sb.Uniform(0, 1), sb.Uniform(50, 500), sb.Uniform(0, 0.5)])),
+        "sir_gillespie_s3": (m.sir_gillespie(83.0, 24.0, 41.7), sb.product_distribution([sb.Uniform(0.1, 1), sb.Uniform(0.05, 0.5)])),
+        "sir_gillespie_s1": (m.sir_gillespie(83.0, 24.0, 41.7, single_stat=True), sb.product_distribution([sb.Uniform(0.1, 1), sb.Uniform(0.05, 0.5)])),
         "sir_tauleap": (m.sir_tauleap(20000.0, 1500.0, 25.0),
                         sb.product_distribution([sb.Uniform(0.1, 1), sb.Uniform(0.05, 0.5), sb.Uniform(0.001, 0.05), sb.Uniform(0.2, 1)])),
     }

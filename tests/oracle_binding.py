@@ -20,11 +20,14 @@ class OrcConfig(C.Structure):
                 ("n_model_par", i32), ("model_par", C.POINTER(dbl)), ("prior_kind", C.POINTER(i32)), ("prior_par", C.POINTER(dbl))]
 
 
-MODEL_IDS = {"gauss_mean": 0, "gauss_sample": 1, "logistic": 2, "sir_tauleap": 3}
+MODEL_IDS = {"gauss_mean": 0, "gauss_sample": 1, "logistic": 2, "sir_tauleap": 3, "sir_gillespie": 4}
 
 
 def model_id(name: str) -> int:
-    return MODEL_IDS["gauss_sample" if name.startswith("gauss_sample") else name]
+    for prefix in ("gauss_sample", "sir_gillespie"):
+        if name.startswith(prefix):
+            return MODEL_IDS[prefix]
+    return MODEL_IDS[name]
 
 
 def build_oracle() -> str:

@@ -39,7 +39,8 @@ def test_c1_gauss_mean_trajectory(gpu):
     assert cnt[0] == 100_000 and cnt[3] == 99 and cnt[2] >= 2 and eps[0] < 0.05
 
 
-@pytest.mark.parametrize("name", ["gauss_sample_d1s1", "gauss_sample_d2s1", "gauss_sample_d1s2", "gauss_sample_d2s2", "logistic", "sir_tauleap"])
+@pytest.mark.parametrize("name", ["gauss_sample_d1s1", "gauss_sample_d2s1", "gauss_sample_d1s2", "gauss_sample_d2s2", "logistic", "sir_tauleap",
+                                  "sir_gillespie_s3", "sir_gillespie_s1"])
 @pytest.mark.parametrize("algorithm", ["single_eps", "multi_eps"])
 def test_models_trajectory(gpu, name, algorithm):
     model, prior = model_cases()[name]
