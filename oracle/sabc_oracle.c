@@ -458,18 +458,22 @@ typedef struct { int32_t kind; double p0, p1, c; } prior1_t;   /* c = log σ  | 
 static void prior_prepare(int32_t d, const int32_t* kind, const double* par, prior1_t* out) {
     for (int32_t c = 0; c < d; ++c) {
         out[c].kind = kind[c]; out[c].p0 = par[2 * c]; out[c].p1 = par[2 * c + 1];
-        out[c].c = kind[c] == ORC_PRIOR_NORMAL ? orc_log(par[2 * c + 1]) : -orc_log(par[2 * c + 1] - par[2 * c]);
+        if (kind[c] == ORC_PRIOR_UNIFORM) out[c].c = -orc_log(par[2 * c + 1] - par[2 * c]);
+        else if (kind[c] == ORC_PRIOR_EXPONENTIAL) out[c].c = orc_log(par[2 * c]);
+        else out[c].c = orc_log(par[2 * c + 1]);
     }
 }
 static double prior_logpdf(int32_t d, const prior1_t* pr, const double* th) {
     double lp = 0.0;
     for (int32_t c = 0; c < d; ++c) {
-        double t;
-        if (pr[c].kind == ORC_PRIOR_NORMAL) {
-            double z = (th[c] - pr[c].p0) / pr[c].p1;
-            t = -((z * z + LOG2PI) * 0.5) - pr[c].c;
-        } else {
-            t = (th[c] >= pr[c].p0 && th[c] <= pr[c].p1) ? pr[c].c : -INFINITY;
+        double t, x = th[c];
+        switch (pr[c].kind) {
+        case ORC_PRIOR_NORMAL: { double z = (x - pr[c].p0) / pr[c].p1; t = -((z * z + LOG2PI) * 0.5) - pr[c].c; break; }
+        case ORC_PRIOR_UNIFORM: t = (x >= pr[c].p0 && x <= pr[c].p1) ? pr[c].c : -INFINITY; break;
+        case ORC_PRIOR_EXPONENTIAL: t = x >= 0.0 ? (-(x / pr[c].p0)) - pr[c].c : -INFINITY; break;
+        default:                                                          /* LogNormal */
+            if (!(x > 0.0)) { t = -INFINITY; break; }
+            { double lx = orc_log(x), z = (lx - pr[c].p0) / pr[c].p1; t = (-((z * z + LOG2PI) * 0.5) - pr[c].c) - lx; }
         }
         lp = (c == 0) ? t : lp + t;
     }
@@ -485,11 +489,12 @@ static void prior_rand(int32_t d, const prior1_t* pr, uint64_t seed, uint32_t pa
     for (int32_t c = 0; c < d; ++c) {
         uint64_t a, b;
         stream_block(&st, (uint32_t)c, &a, &b);
-        if (pr[c].kind == ORC_PRIOR_NORMAL) {
-            double z0, z1; orc_normal_pair(a, b, &z0, &z1);
-            th[c] = pr[c].p0 + pr[c].p1 * z0;
-        } else {
-            th[c] = pr[c].p0 + (pr[c].p1 - pr[c].p0) * u53(a);
+        double z0, z1;
+        switch (pr[c].kind) {
+        case ORC_PRIOR_NORMAL: orc_normal_pair(a, b, &z0, &z1); th[c] = pr[c].p0 + pr[c].p1 * z0; break;
+        case ORC_PRIOR_UNIFORM: th[c] = pr[c].p0 + (pr[c].p1 - pr[c].p0) * u53(a); break;
+        case ORC_PRIOR_EXPONENTIAL: th[c] = pr[c].p0 * (-orc_log(u53_open0(a))); break;
+        default: orc_normal_pair(a, b, &z0, &z1); th[c] = orc_exp(pr[c].p0 + pr[c].p1 * z0); break;
         }
     }
 }

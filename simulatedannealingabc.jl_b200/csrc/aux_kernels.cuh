@@ -133,14 +133,7 @@ static __global__ void k_recompute_lp(PopView pop, int64_t r0, int64_t r1, int D
     for (int64_t i = r0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += (int64_t)gridDim.x * blockDim.x) {
         double lp = 0.0;
         for (int c = 0; c < D; ++c) {
-            const double x = pop.theta[c * pop.ld + i];
-            double t;
-            if (prior.kind[c] == PRIOR_NORMAL) {
-                const double z = (x - prior.p0[c]) / prior.p1[c];
-                t = -((z * z + 0x1.d67f1c864beb5p+0) * 0.5) - prior.c[c];
-            } else {
-                t = (x >= prior.p0[c] && x <= prior.p1[c]) ? prior.c[c] : -dinf();
-            }
+            const double t = prior_logpdf1(prior.kind[c], prior.p0[c], prior.p1[c], prior.c[c], pop.theta[c * pop.ld + i]);
             lp = (c == 0) ? t : lp + t;
         }
         pop.lp[i] = lp;

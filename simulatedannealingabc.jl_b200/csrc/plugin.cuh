@@ -22,7 +22,7 @@ constexpr int CHUNK = 256;          // particles per tree-sum group == threads p
 
 enum Algorithm : int32_t { ALG_SINGLE_EPS = 0, ALG_MULTI_EPS = 1 };
 enum ProposalKind : int32_t { PROP_DE = 0, PROP_STRETCH = 1, PROP_RW = 2 };
-enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1 };
+enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1, PRIOR_EXPONENTIAL = 2, PRIOR_LOGNORMAL = 3 };
 
 // ------------------------------------------------------------------------------------------------
 // Prior: product of independent univariates (Distributions ^0.25 formulas)
@@ -30,13 +30,33 @@ enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1 };
 struct PriorSpec {
     int32_t n;
     int32_t kind[MAX_D];
-    double p0[MAX_D], p1[MAX_D];   // Uniform(a,b) | Normal(mu,sigma)
-    double c[MAX_D];               // -log(b-a)    | log(sigma)   (det_log, filled by prior_prepare)
+    double p0[MAX_D], p1[MAX_D];   // Uniform(a,b) | Normal(mu,sigma) | Exponential(theta,-) | LogNormal(mu,sigma)
+    double c[MAX_D];               // -log(b-a)    | log(sigma)       | log(theta)           | log(sigma)   (det_log)
 };
 
 inline void prior_prepare(PriorSpec& p) {
-    for (int i = 0; i < p.n; ++i)
-        p.c[i] = p.kind[i] == PRIOR_NORMAL ? det_log(p.p1[i]) : -det_log(p.p1[i] - p.p0[i]);
+    for (int i = 0; i < p.n; ++i) {
+        switch (p.kind[i]) {
+            case PRIOR_UNIFORM: p.c[i] = -det_log(p.p1[i] - p.p0[i]); break;
+            case PRIOR_EXPONENTIAL: p.c[i] = det_log(p.p0[i]); break;
+            default: p.c[i] = det_log(p.p1[i]); break;
+        }
+    }
+}
+
+// log-density of one univariate component (Distributions ^0.25 formulas)
+SABC_HD double prior_logpdf1(int kind, double p0, double p1, double c, double x) {
+    const double LOG2PI = 0x1.d67f1c864beb5p+0;
+    if (kind == PRIOR_NORMAL) {
+        const double z = (x - p0) / p1;
+        return -((z * z + LOG2PI) * 0.5) - c;
+    }
+    if (kind == PRIOR_UNIFORM) return (x >= p0 && x <= p1) ? c : -dinf();
+    if (kind == PRIOR_EXPONENTIAL) return x >= 0.0 ? (-(x / p0)) - c : -dinf();
+    if (!(x > 0.0)) return -dinf();                         // LogNormal
+    const double lx = det_log(x);
+    const double z = (lx - p0) / p1;
+    return (-((z * z + LOG2PI) * 0.5) - c) - lx;
 }
 
 template <int D>
@@ -44,14 +64,8 @@ SABC_HD double prior_logpdf(const PriorSpec& p, const double (&th)[D]) {
     double lp = 0.0;
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-        double t;
-        if (p.kind[c] == PRIOR_NORMAL) {
-            const double z = (th[c] - p.p0[c]) / p.p1[c];
-            t = -((z * z + 0x1.d67f1c864beb5p+0) * 0.5) - p.c[c];
-        } else {
-            t = (th[c] >= p.p0[c] && th[c] <= p.p1[c]) ? p.c[c] : -dinf();
-        }
-        lp = (c == 0) ? t : lp + t;
+        const double t = prior_logpdf1(p.kind[c], p.p0[c], p.p1[c], p.c[c], th[c]);
+        lp = (c == 0) ? t : lp + t;                          // product distribution: sum of the components
     }
     return lp;
 }
@@ -62,11 +76,12 @@ SABC_HD void prior_rand(const PriorSpec& p, uint64_t seed, uint32_t particle, do
 #pragma unroll
     for (int c = 0; c < D; ++c) {
         const U64x2 w = st.block((uint32_t)c);
-        if (p.kind[c] == PRIOR_NORMAL) {
-            double z0, z1; normal_pair(w, z0, z1);
-            th[c] = p.p0[c] + p.p1[c] * z0;
-        } else {
-            th[c] = p.p0[c] + (p.p1[c] - p.p0[c]) * u53(w.a);
+        double z0, z1;
+        switch (p.kind[c]) {
+            case PRIOR_NORMAL: normal_pair(w, z0, z1); th[c] = p.p0[c] + p.p1[c] * z0; break;
+            case PRIOR_UNIFORM: th[c] = p.p0[c] + (p.p1[c] - p.p0[c]) * u53(w.a); break;
+            case PRIOR_EXPONENTIAL: th[c] = p.p0[c] * (-det_log(u53_open0(w.a))); break;
+            default: normal_pair(w, z0, z1); th[c] = det_exp(p.p0[c] + p.p1[c] * z0); break;
         }
     }
 }

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
-PRIOR_UNIFORM, PRIOR_NORMAL = 0, 1
+PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_EXPONENTIAL, PRIOR_LOGNORMAL = 0, 1, 2, 3
 
 
 class Distribution:
@@ -46,11 +46,43 @@ class Normal(Distribution):
         return (float(self.mu), float(self.sigma))
 
 
+@dataclass(frozen=True)
+class Exponential(Distribution):
+    theta: float = 1.0            # scale, as in Distributions.Exponential(θ)
+
+    def __post_init__(self):
+        if not self.theta > 0:
+            raise ValueError("Exponential: the condition θ > 0 is not satisfied")
+
+    kind = PRIOR_EXPONENTIAL
+
+    def params(self):
+        return (float(self.theta), 0.0)
+
+
+@dataclass(frozen=True)
+class LogNormal(Distribution):
+    mu: float = 0.0
+    sigma: float = 1.0
+
+    def __post_init__(self):
+        if not self.sigma > 0:
+            raise ValueError("LogNormal: the condition σ > 0 is not satisfied")
+
+    kind = PRIOR_LOGNORMAL
+
+    def params(self):
+        return (float(self.mu), float(self.sigma))
+
+
+UNIVARIATE = (Uniform, Normal, Exponential, LogNormal)
+
+
 class Product(Distribution):
     def __init__(self, dists):
         self.dists = list(dists)
-        if not self.dists or not all(isinstance(d, (Uniform, Normal)) for d in self.dists):
-            raise TypeError("product_distribution supports Uniform and Normal components on the device path")
+        if not self.dists or not all(isinstance(d, UNIVARIATE) for d in self.dists):
+            raise TypeError("product_distribution supports Uniform, Normal, Exponential and LogNormal components on the device path")
 
     def components(self):
         return self.dists

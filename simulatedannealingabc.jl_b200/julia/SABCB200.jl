@@ -9,7 +9,7 @@ module SABCB200
 using SimulatedAnnealingABC
 import SimulatedAnnealingABC: sabc, update_population!, SABCresult, SABCstate, Proposal,
                               DifferentialEvolution, StretchMove, RandomWalk
-using Distributions: Distribution, Uniform, Normal, Product, params
+using Distributions: Distribution, Uniform, Normal, Exponential, LogNormal, Product, params
 
 const libsabc = get(ENV, "SABC_B200_LIB", joinpath(@__DIR__, "..", "libsabc_b200.so"))
 
@@ -44,9 +44,10 @@ sir_tauleap(obs_total, obs_peak, obs_tpeak; pop=1e5, n_steps=50, τ=1.0) =
     DeviceModel("sir_tauleap", 4, 3, [pop, n_steps, τ, obs_total, obs_peak, obs_tpeak])
 
 # ---- plug-in encodings ----
-prior_components(p::Union{Uniform,Normal}) = [p]
+prior_components(p::Union{Uniform,Normal,Exponential,LogNormal}) = [p]
 prior_components(p::Product) = collect(p.v)
-prior_kind(::Uniform) = Int32(0); prior_kind(::Normal) = Int32(1)
+prior_kind(::Uniform) = Int32(0); prior_kind(::Normal) = Int32(1); prior_kind(::Exponential) = Int32(2); prior_kind(::LogNormal) = Int32(3)
+prior_params(c) = (p = params(c); length(p) == 2 ? (p[1], p[2]) : (p[1], 0.0))
 proposal_code(p::DifferentialEvolution) = (Int32(0), (p.γ0, p.σ_gamma))
 proposal_code(p::StretchMove) = (Int32(1), (p.a, 0.0))
 proposal_code(p::RandomWalk) = (Int32(2), (p.β, 0.0))
@@ -61,7 +62,7 @@ function Engine(model::DeviceModel, prior::Distribution; n_particles, algorithm,
     comps = prior_components(prior)
     length(comps) == model.n_para || error("prior has $(length(comps)) components, model $(model.name) has $(model.n_para) parameters")
     kinds = Int32[prior_kind(c) for c in comps]
-    ppar = Float64[x for c in comps for x in params(c)]
+    ppar = Float64[x for c in comps for x in prior_params(c)]
     pcode, ppars = proposal_code(proposal)
     alg = algorithm == :multi_eps ? Int32(1) : Int32(0)
     h = Ref{Ptr{Cvoid}}(C_NULL)

@@ -175,6 +175,17 @@ def test_prior_logpdf(gpu):
     assert np.all(np.isneginf(lp[~inside])) and np.all(np.isfinite(lp[inside]))
     ref = -0.5 * ((th[:, 0] - 0.5) / 2) ** 2 - 0.5 * np.log(2 * np.pi) - np.log(2.0) - np.log(4.0) - np.log(0.5)
     assert np.allclose(lp[inside], ref[inside], rtol=1e-13)
+    # Exponential(theta) and LogNormal(mu, sigma) against scipy
+    from scipy import stats
+    kind = np.array([2, 3], dtype=np.int32); par = np.array([1.5, 0.0, 0.5, 0.8])
+    th = np.asfortranarray(np.column_stack([rng.uniform(-1, 6, 4000), rng.uniform(-0.5, 8, 4000)]))
+    lp = np.zeros(4000)
+    L.check(L.lib().sabc_prior_logpdf(2, ptr(kind), ptr(par), ptr(th), 4000, ptr(lp)))
+    want = np.array([ob.lib().orc_prior_logpdf(2, ob.p(kind), ob.p(par), ob.p(np.ascontiguousarray(th[i]))) for i in range(4000)])
+    assert np.array_equal(lp, want)
+    ok = (th[:, 0] >= 0) & (th[:, 1] > 0)
+    ref = stats.expon(scale=1.5).logpdf(th[ok, 0]) + stats.lognorm(s=0.8, scale=np.exp(0.5)).logpdf(th[ok, 1])
+    assert np.allclose(lp[ok], ref, rtol=1e-12, atol=1e-12) and np.all(np.isneginf(lp[~ok]))
 
 
 @pytest.mark.parametrize("name", list(model_cases().keys()))
@@ -183,7 +194,12 @@ def test_model_simulate_bit_exact(gpu, name):
     rng = np.random.default_rng(11)
     n = 3000
     comps = prior.components()
-    th = np.column_stack([rng.normal(c.mu, c.sigma, n) if isinstance(c, sb.Normal) else rng.uniform(c.a, c.b, n) for c in comps])
+    def draw(c):
+        if isinstance(c, sb.Normal): return rng.normal(c.mu, c.sigma, n)
+        if isinstance(c, sb.Uniform): return rng.uniform(c.a, c.b, n)
+        if isinstance(c, sb.Exponential): return rng.exponential(c.theta, n)
+        return rng.lognormal(c.mu, c.sigma, n)
+    th = np.column_stack([draw(c) for c in comps])
     rho = model.simulate(th, seed=123, particle_base=1000, sweep=7)
     par = np.ascontiguousarray(model.par)
     want = np.zeros((n, model.n_stats)); tmp = np.zeros(model.n_stats)

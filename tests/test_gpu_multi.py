@@ -99,6 +99,13 @@ eng.init(); eng.update(400 * N)
 th = np.concatenate(gather(eng.get_population()[0]))[:, 0]
 report["c1_posterior"] = {"mean": float(th.mean()), "var": float(th.var())}
 assert abs(th.mean() - 10 / 11) < 0.02 and abs(th.var() - 1 / 11) < 0.01, report["c1_posterior"]
+# the mirrored public surface over the sharded engine: sabc(...; comm="torch") then update_population
+f2, p2 = model_cases()["gauss_sample_d2s2"]
+res = sb.sabc(f2, p2, n_particles=500 * world, n_simulation=5000 * world, algorithm="multi_eps", comm="torch", device=int(os.environ["LOCAL_RANK"]))
+assert res.state.n_population_updates == 9 and res.population.shape == (500, 2) and np.all(res.state.eps < 1)
+sb.update_population(res, f2, p2, n_simulation=5000 * world)
+assert res.state.n_population_updates == 19 and res.state.n_simulation == 500 * world * 20
+states = gather([res.state.eps.tolist(), res.state.n_accept, res.state.n_resampling]); assert all(x == states[0] for x in states)
 if rank == 0:
     print("REPORT " + json.dumps(report))
 dist.barrier()
