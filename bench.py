@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer (e2e) leg; default min(steps, 50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="extra SABC_FLAG_* bits for the engine (tuning)")
     ap.add_argument("--graph", action="store_true", help="replay the CUDA graph in the timed region (kernel times then come from a separate pass)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -219,7 +220,7 @@ def main():
 
     N = n_per_gpu * world
     time_kernels_live = not args.graph and world == 1
-    flags = sb.SABC_FLAG_TIME_KERNELS if time_kernels_live else 0
+    flags = (sb.SABC_FLAG_TIME_KERNELS if time_kernels_live else 0) | args.flags
     kw = dict(n_particles=N, algorithm=algorithm, proposal=sb.DifferentialEvolution(n_para=d), resample=2 * N, v=1.0, delta=0.1,
               device=local_rank)
     comm = sb.api._distributed_setup("torch") if world > 1 else (0, 1, None)

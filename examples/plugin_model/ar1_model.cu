@@ -10,7 +10,8 @@
 
 struct Ar1Model {
     static constexpr int D = 2, S = 2;
-    static constexpr int SIM_MIN_BLOCKS = 1;
+    static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel (split path)
+    static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[2], const sabc::ModelPar& mp, sabc::Stream& st, double (&rho)[2]) {
         const int T = (int)mp.v[0];
         double x = 0.0, s1 = 0.0, s2 = 0.0, sx = 0.0;

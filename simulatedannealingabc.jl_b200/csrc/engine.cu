@@ -95,7 +95,9 @@ struct sabc_engine {
     DevBuf<unsigned long long> b_q, b_tile_sum, b_tile_off;
     DevBuf<double> b_rho_part, b_scratch, b_rw_part, b_rw_sums, b_hist;
     DevBuf<double> b_sp_theta, b_sp_lp, b_sp_lf;      // split path work list
-    DevBuf<uint32_t> b_sp_idx;
+    DevBuf<uint32_t> b_sp_idx, b_sp_key, b_sp_perm;
+    DevBuf<unsigned int> b_sp_hist, b_sp_off;
+    bool sort_work = false;
     bool split = false;
     int grid_simacc = 0, bps_simacc = 0;
 
@@ -243,6 +245,7 @@ static SplitScratch make_split(sabc_engine* e) {
     w.theta = e->b_sp_theta.p; w.lp = e->b_sp_lp.p; w.lf = e->b_sp_lf.p; w.idx = e->b_sp_idx.p;
     w.count = &e->b_ds.p->list_count[0]; w.cursor = &e->b_ds.p->list_cursor[0];
     w.cap = e->n_local - e->n_local / 2;
+    if (e->sort_work) { w.key = e->b_sp_key.p; w.perm = e->b_sp_perm.p; w.hist = e->b_sp_hist.p; w.off = e->b_sp_off.p; }
     return w;
 }
 static int launch_update_half(sabc_engine* e, int half, int sub = 0, int nsub = 1) {
@@ -256,7 +259,14 @@ static int launch_split_propose(sabc_engine* e, int half, int sub = 0, int nsub 
     const UpdateArgs a = make_update_args(e, half, sub, nsub);
     if (a.act_n <= 0) return 0;
     const int64_t groups = (a.act_n + CHUNK - 1) / CHUNK;
-    SABC_CUDA(e->model->launch_propose(e->proposal, a, make_split(e), (int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), e->stream));
+    const SplitScratch w = make_split(e);
+    SABC_CUDA(e->model->launch_propose(e->proposal, a, w, (int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), e->stream));
+    if (e->sort_work) {                // group the work list by the model's similarity key
+        bucket_scan_kernel<<<1, 1024, 0, e->stream>>>(w.hist, w.off);
+        bucket_scatter_kernel<<<(int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), CHUNK, 0, e->stream>>>(w.key, w.count, a.slot, w.hist, w.off, w.perm);
+        bucket_clear_kernel<<<1, 1024, 0, e->stream>>>(w.hist);
+        SABC_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 static int launch_split_simacc(sabc_engine* e, int half, int sub = 0, int nsub = 1) {
@@ -333,7 +343,7 @@ static int launch_finish(sabc_engine* e) {
     return 0;
 }
 
-static int kernels_per_iteration(const sabc_engine* e) { return (e->split ? 6 : 2) + 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1; }
+static int kernels_per_iteration(const sabc_engine* e) { return (e->split ? 6 : 2) + (e->sort_work ? 6 : 0) + 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1; }
 
 // the two half-sweeps (:304-332) in the fused or the split form.  A pipelined host call cuts each half into sub-ranges
 // (identical results: the particles of a half-sweep are independent) so that transfers overlap at a finer grain.
@@ -506,6 +516,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     if (e->flags & SABC_FLAG_TIME_KERNELS) e->flags |= SABC_FLAG_NO_GRAPH;
     if (world > 1) e->flags |= SABC_FLAG_NO_GRAPH;
     e->split = model->heavy && !(e->flags & SABC_FLAG_FUSED);
+    e->sort_work = e->split && model->key_bits > 0 && (e->flags & SABC_FLAG_SORT_WORK);
     e->device = dev; e->model = model;
     for (int k = 0; k < c->n_model_par; ++k) e->mp.v[k] = c->model_par[k];
     e->prior.n = e->D;
@@ -530,7 +541,9 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     A(e->b_ttheta.alloc(n * e->D)); A(e->b_tu.alloc(n * e->S)); A(e->b_tlp.alloc(n));
     A(e->b_ds.alloc(1)); A(e->b_ecdf.alloc(MAX_S));
     A(e->b_q.alloc(n));
-    { const size_t cap = n - n / 2; A(e->b_sp_theta.alloc(cap * e->D)); A(e->b_sp_lp.alloc(cap)); A(e->b_sp_lf.alloc(cap)); A(e->b_sp_idx.alloc(cap)); }
+    { const size_t cap = n - n / 2; A(e->b_sp_theta.alloc(cap * e->D)); A(e->b_sp_lp.alloc(cap)); A(e->b_sp_lf.alloc(cap)); A(e->b_sp_idx.alloc(cap));
+      A(e->b_sp_key.alloc(cap)); A(e->b_sp_perm.alloc(cap)); A(e->b_sp_hist.alloc(WORK_BUCKETS)); A(e->b_sp_off.alloc(WORK_BUCKETS));
+      if (ce == cudaSuccess) ce = cudaMemsetAsync(e->b_sp_hist.p, 0, WORK_BUCKETS * sizeof(unsigned int), e->stream); }
     const int64_t n_tiles = ((int64_t)n + TILE - 1) / TILE;
     A(e->b_tile_sum.alloc((size_t)n_tiles)); A(e->b_tile_off.alloc((size_t)n_tiles));
     e->part_ld = ((int64_t)n + CHUNK - 1) / CHUNK + 1;

@@ -188,7 +188,13 @@ struct SplitScratch {
     unsigned int* count;      // [MAX_SLOTS] entries per (half, sub-range)
     unsigned int* cursor;     // [MAX_SLOTS] dynamic work cursor of the simulation kernel
     int64_t cap;
+    // optional bucketing of the work list by a model-supplied similarity key (lanes of a warp then simulate alike)
+    uint32_t* key;            // [cap] bucket of entry q, or nullptr
+    uint32_t* perm;           // [cap] simulation order: position -> entry
+    unsigned int* hist;       // [WORK_BUCKETS] bucket sizes, then scatter cursors
+    unsigned int* off;        // [WORK_BUCKETS] bucket offsets
 };
+constexpr int WORK_BUCKETS = 4096;
 
 struct InitArgs {
     PopView pop;
@@ -354,6 +360,13 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, cons
 #pragma unroll
             for (int c = 0; c < D; ++c) w.theta[c * w.cap + q] = thp[c];
             w.lp[q] = lpp; w.lf[q] = lf; w.idx[q] = (uint32_t)il;
+            if constexpr (M::KEY_BITS > 0) {
+                if (w.key) {
+                    const uint32_t key = M::work_key(thp, a.mp) & (WORK_BUCKETS - 1);
+                    w.key[q] = key;
+                    atomicAdd(&w.hist[key], 1u);
+                }
+            }
         }
     }
 }
@@ -376,9 +389,10 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
         if (lane == 0) q0 = atomicAdd(&w.cursor[a.slot], 32u);
         q0 = __shfl_sync(0xffffffffu, q0, 0);
         if (q0 >= n_items) break;
-        const unsigned q = q0 + lane;
-        const unsigned live = __ballot_sync(0xffffffffu, q < n_items);
-        if (q < n_items) {
+        const unsigned pos = q0 + lane;
+        const unsigned live = __ballot_sync(0xffffffffu, pos < n_items);
+        if (pos < n_items) {
+            const unsigned q = (M::KEY_BITS > 0 && w.perm) ? w.perm[pos] : pos;
             const int64_t gi = a.act_off + (int64_t)w.idx[q];
             const uint32_t pid = a.particle_base + (uint32_t)gi;
             double thp[D], rp[S], up[S];
@@ -409,6 +423,48 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
     }
     n_acc = __reduce_add_sync(0xffffffffu, n_acc);
     if (lane == 0 && n_acc) atomicAdd(&a.ds->n_acc_iter, (unsigned long long)n_acc);
+}
+
+// bucket offsets (exclusive scan of the histogram) by one CTA; the histogram is cleared for its second use as cursors
+static __global__ void __launch_bounds__(1024) bucket_scan_kernel(unsigned int* hist, unsigned int* off) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < WORK_BUCKETS; base += 1024) {
+        const unsigned int v = hist[base + threadIdx.x];
+        unsigned int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int x = s_warp[lane], xi = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+            s_warp[lane] = xi - x;
+        }
+        __syncthreads();
+        const unsigned int excl = s_carry + s_warp[wid] + inc - v;
+        off[base + threadIdx.x] = excl;
+        hist[base + threadIdx.x] = 0u;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+// simulation order: entries grouped by bucket (the order inside a bucket is irrelevant to the result)
+static __global__ void bucket_scatter_kernel(const uint32_t* key, const unsigned int* count, int slot, unsigned int* cursor,
+                                             const unsigned int* off, uint32_t* perm) {
+    const unsigned int n = count[slot];
+    for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t k = key[q];
+        perm[off[k] + atomicAdd(&cursor[k], 1u)] = q;
+    }
+}
+static __global__ void bucket_clear_kernel(unsigned int* hist) {
+    for (int i = threadIdx.x; i < WORK_BUCKETS; i += blockDim.x) hist[i] = 0u;
 }
 
 // Σu limbs and per-group ρ tree sums of one half after the split update (generic in S)
@@ -494,6 +550,7 @@ struct ModelVTable {
     cudaError_t (*launch_update)(int proposal, const UpdateArgs&, int grid, size_t smem, cudaStream_t);
     cudaError_t (*update_occupancy)(int proposal, size_t smem, int* blocks_per_sm);
     int32_t heavy;            // 1: use the split path (propose -> compacted simulate+accept -> stats)
+    int32_t key_bits;         // > 0: the model supplies a similarity key for work-list bucketing
     cudaError_t (*launch_propose)(int proposal, const UpdateArgs&, const SplitScratch&, int grid, cudaStream_t);
     cudaError_t (*launch_simacc)(const UpdateArgs&, const SplitScratch&, int grid, size_t smem, cudaStream_t);
     cudaError_t (*simacc_occupancy)(size_t smem, int* blocks_per_sm);
@@ -569,7 +626,7 @@ struct ModelLaunchers {
         ModelVTable v{};
         v.name = name; v.n_para = M::D; v.n_stats = M::S;
         v.launch_init = &init; v.launch_update = &update; v.update_occupancy = &occupancy; v.simulate = &simulate;
-        v.heavy = heavy; v.launch_propose = &propose; v.launch_simacc = &simacc; v.simacc_occupancy = &simacc_occ;
+        v.heavy = heavy; v.key_bits = M::KEY_BITS; v.launch_propose = &propose; v.launch_simacc = &simacc; v.simacc_occupancy = &simacc_occ;
         return v;
     }
 };

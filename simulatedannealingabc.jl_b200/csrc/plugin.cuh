@@ -239,6 +239,7 @@ struct ModelPar { double v[MAX_MODEL_PAR]; };
 struct GaussMean {
     static constexpr int D = 1, S = 1;
     static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
+    static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[1], const ModelPar& mp, Stream& st, double (&rho)[1]) {
         double z0, z1; normal_pair(st.draw(), z0, z1);
         const double ysim = th[0] + mp.v[1] * z0;
@@ -252,6 +253,7 @@ template <int D_, int S_>
 struct GaussSample {
     static constexpr int D = D_, S = S_;
     static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
+    static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[D_], const ModelPar& mp, Stream& st, double (&rho)[S_]) {
         const int n = (int)mp.v[0];
         const double sig = D_ >= 2 ? th[D_ - 1] : mp.v[1];
@@ -271,6 +273,7 @@ struct GaussSample {
 struct Logistic {
     static constexpr int D = 3, S = 20;
     static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
+    static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[3], const ModelPar& mp, Stream& st, double (&rho)[20]) {
         double x = mp.v[0];
 #pragma unroll
@@ -292,6 +295,14 @@ struct Logistic {
 struct SirTauLeap {
     static constexpr int D = 4, S = 3;
     static constexpr int SIM_MIN_BLOCKS = 4;   // cap at 64 registers: 32 warps per SM hide the FP64 latencies
+    // similarity key of a proposal for the work-list bucketing: growth rate β−γ (6 bits), initial fraction ι (3), γ (3).
+    // Particles of one bucket have similar epidemic curves, so the lanes of a warp meet the same sampler regimes and
+    // finish together.  The key only orders the work; it never enters the arithmetic.
+    static constexpr int KEY_BITS = 12;
+    SABC_HD static uint32_t work_key(const double (&th)[4], const ModelPar&) {
+        auto q = [](double x, double lo, double hi, int n) { int v = (int)((x - lo) / (hi - lo) * (double)n); return (uint32_t)(v < 0 ? 0 : (v >= n ? n - 1 : v)); };
+        return (q(th[0] - th[1], -0.4, 0.95, 64) << 6) | (q(th[2], 0.001, 0.05, 8) << 3) | q(th[1], 0.05, 0.5, 8);
+    }
     // Per step: n_inf ~ Poisson(β S I/pop τ) ∧ S, n_rec ~ Poisson(γ I τ) ∧ I, cases ~ Poisson(φ n_inf).  Written as a
     // per-lane state machine over sampler ATTEMPTS (phase 0/1/2 = the three draws of a step): every loop trip each
     // lane makes one attempt on its own current draw, so a PTRS rejection costs that lane one trip instead of
@@ -346,6 +357,7 @@ template <int S_>
 struct SirGillespie {
     static constexpr int D = 2, S = S_;
     static constexpr int SIM_MIN_BLOCKS = 4;
+    static constexpr int KEY_BITS = 0;
     SABC_HD static void sim(const double (&th)[2], const ModelPar& mp, Stream& st, double (&rho)[S_]) {
         double Sc = mp.v[0], I = mp.v[1], R = mp.v[2];
         const double tmax = mp.v[3], Npop = (Sc + I) + R;

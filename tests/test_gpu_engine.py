@@ -90,7 +90,7 @@ def test_split_and_fused_kernels_agree(gpu, name, prop):
     kernel.  Both must reproduce the oracle bit for bit."""
     model, prior = model_cases()[name]
     proposal = {"de": DE(model.n_para), "stretch": sb.StretchMove(), "rw": sb.RandomWalk(n_para=model.n_para)}[prop]
-    for flags in (0, sb.SABC_FLAG_FUSED, sb.SABC_FLAG_NO_GRAPH, sb.SABC_FLAG_FUSED | sb.SABC_FLAG_TIME_KERNELS):
+    for flags in (0, sb.SABC_FLAG_FUSED, sb.SABC_FLAG_NO_GRAPH, sb.SABC_FLAG_FUSED | sb.SABC_FLAG_TIME_KERNELS, sb.SABC_FLAG_SORT_WORK):
         run_pair(model, prior, 1500, 8, proposal=proposal, resample=1500, flags=flags)
 
 
