@@ -227,3 +227,36 @@ def test_posterior_matches_conjugate_and_oracle(gpu):
     # thin to reduce the within-run correlation the KS test ignores
     p = stats.ks_2samp(pops[0][::8], tho[::8]).pvalue
     assert p > 0.01, p
+
+
+@pytest.mark.parametrize("name,N,alg", [("sir_tauleap", 1_250_000, "single_eps"), ("gauss_mean", 10_000_000, "single_eps"),
+                                        ("logistic", 1_000_000, "single_eps"), ("gauss_sample_d2s2", 100_000, "multi_eps")])
+def test_full_size_properties(gpu, name, N, alg):
+    """BASELINE.json sizes (per GPU), where the oracle would take minutes: size-independent properties instead -- determinism
+    (graph replay == direct launches, run twice), the exact integer means equal the means of the downloaded population, every
+    particle inside the prior support, u in [0,1], sorted ECDF knots with L = n_positive + 2, counters."""
+    model, prior = model_cases()[name]
+    kw = dict(n_particles=N, algorithm=alg, proposal=DE(model.n_para), resample=N // 2, v=1.0, delta=0.1)
+    outs = []
+    for flags in (0, sb.SABC_FLAG_NO_GRAPH):
+        eng = sb.Engine(model, prior, flags=flags, **kw)
+        eng.init()
+        th0, u0, rho0 = eng.get_population()
+        for j in range(model.n_stats):
+            k = eng.get_ecdf(j)
+            assert k[0] == 0.0 and np.all(np.diff(k) >= 0) and k[-1] == 1.5 * k[-2] and k.size == np.count_nonzero(rho0[:, j] > 0) + 2
+        eng.update(4 * N)
+        outs.append((eng.get_population(), eng.get_state(), eng.get_history()))
+        eng.close()
+    (th, u, rho), (eps, cnt), (eh, uh, rh) = outs[0]
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(outs[0][1][0], outs[1][1][0]) and np.array_equal(outs[0][1][1], outs[1][1][1])
+    assert cnt[0] == 5 * N and cnt[3] == 4 and cnt[2] >= 2 and 0 < cnt[1] < 4 * N
+    assert np.all((u >= 0) & (u <= 1 + 1e-15)) and np.all(rho >= 0) and np.all(np.isfinite(th))
+    for c, comp in enumerate(prior.components()):
+        if isinstance(comp, sb.Uniform):
+            assert th[:, c].min() >= comp.a and th[:, c].max() <= comp.b
+    assert np.allclose(uh[-1], u.mean(axis=0), rtol=1e-12, atol=0)
+    assert np.allclose(rh[-1], rho.mean(axis=0), rtol=1e-9, atol=0)
+    assert np.all(np.diff(eh[:, 0]) < 0) and np.all(eps > 0)            # eps anneals monotonically in these runs
