@@ -236,7 +236,7 @@ def test_full_size_properties(gpu, name, N, alg):
     (graph replay == direct launches, run twice), the exact integer means equal the means of the downloaded population, every
     particle inside the prior support, u in [0,1], sorted ECDF knots with L = n_positive + 2, counters."""
     model, prior = model_cases()[name]
-    kw = dict(n_particles=N, algorithm=alg, proposal=DE(model.n_para), resample=N // 2, v=1.0, delta=0.1)
+    kw = dict(n_particles=N, algorithm=alg, proposal=DE(model.n_para), resample=N // 16, v=1.0, delta=0.1)
     outs = []
     for flags in (0, sb.SABC_FLAG_NO_GRAPH):
         eng = sb.Engine(model, prior, flags=flags, **kw)
