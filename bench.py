@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer (e2e) leg; default min(steps, 50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ecdf-knots", type=int, default=0, help="compressed ECDF mode: keep K quantiles (0 = the reference's full ECDF)")
     ap.add_argument("--flags", type=int, default=0, help="extra SABC_FLAG_* bits for the engine (tuning)")
     ap.add_argument("--graph", action="store_true", help="replay the CUDA graph in the timed region (kernel times then come from a separate pass)")
     args = ap.parse_args()
@@ -224,6 +225,7 @@ def main():
     kw = dict(n_particles=N, algorithm=algorithm, proposal=sb.DifferentialEvolution(n_para=d), resample=2 * N, v=1.0, delta=0.1,
               device=local_rank)
     comm = sb.api._distributed_setup("torch") if world > 1 else (0, 1, None)
+    kw["ecdf_max_knots"] = args.ecdf_knots
     eng = sb.Engine(model, prior, rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], flags=flags, **kw)
     eng.init()
 
@@ -309,7 +311,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "particles_per_gpu": n_per_gpu, "n_particles": N, "n_para": d, "n_stats": s, "algorithm": algorithm,
-                   "proposal": "DifferentialEvolution", "resample": 2 * N, "checkpoint_history": 1,
+                   "proposal": "DifferentialEvolution", "resample": 2 * N, "checkpoint_history": 1, "ecdf_max_knots": args.ecdf_knots,
                    "rng": "Philox4x32-10 counter streams", "accept_fraction": accept_frac,
                    "l2": f"per-GPU working set {(8 * nl * (d + 2 * s + 1) + 8 * s * (N + 2)) / 1e6:.0f} MB (state + ECDF tables) vs 126 MB L2; no explicit flush",
                    "launch": "direct launches with event pairs" if time_kernels_live else ("host-driven + NCCL" if world > 1 else "CUDA graph replay")},

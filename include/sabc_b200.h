@@ -69,6 +69,10 @@ typedef struct sabc_config {
     int32_t  rank, world_size;
     const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; NULL when world_size == 1 */
     uint32_t flags;           /* SABC_FLAG_* */
+    /* 0 = the reference's ECDF over the whole prior sample (src/cdf_estimators.jl:23-44).  K >= 2: compressed mode, the table
+     * keeps K rank-uniform quantiles of the positive prior distances (plus 0 and 1.5 max) and fits into shared memory as a whole;
+     * an approximation of order 1/K that the oracle reproduces when given the same K. */
+    int32_t  ecdf_max_knots;
 } sabc_config;
 
 #define SABC_FLAG_NO_GRAPH      1u  /* launch kernels directly instead of replaying a CUDA graph */

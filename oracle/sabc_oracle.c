@@ -796,6 +796,15 @@ int orc_init(orc_engine* e) {
         free(e->knots[j]); e->knots[j] = malloc((size_t)(N + 2) * sizeof(double));
         e->L[j] = orc_ecdf_build(col, N, e->knots[j]);
         if (e->L[j] < 0) { free(col); return fail(-8, "build_cdf: no positive prior distance for a statistic"); }
+        int64_t K = e->cfg.ecdf_max_knots, m = e->L[j] - 2;
+        if (K >= 2 && m > K) {                 /* compressed mode: x[floor(i (m-1)/(K-1))], i = 0..K-1 */
+            double* kn = e->knots[j];
+            double* small = malloc((size_t)(K + 2) * sizeof(double));
+            small[0] = 0.0;
+            for (int64_t i = 0; i < K; ++i) small[1 + i] = kn[1 + (i * (m - 1)) / (K - 1)];
+            small[K + 1] = kn[m] * 1.5;
+            free(kn); e->knots[j] = small; e->L[j] = K + 2;
+        }
     }
     free(col);
     #pragma omp parallel for schedule(static)

@@ -46,6 +46,7 @@ typedef struct orc_config {
     const double* model_par;
     const int32_t* prior_kind;   /* n_para entries */
     const double* prior_par;     /* 2*n_para entries */
+    int32_t ecdf_max_knots;      /* 0: full ECDF; K >= 2: K rank-uniform quantiles (compressed mode of the product) */
 } orc_config;
 
 typedef struct orc_engine orc_engine;

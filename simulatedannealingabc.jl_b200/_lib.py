@@ -40,7 +40,7 @@ class Config(C.Structure):
         ("proposal", C.c_int32), ("prop_par", C.c_double * 2), ("v", C.c_double), ("delta", C.c_double),
         ("resample", C.c_int64), ("seed", C.c_uint64), ("model_name", C.c_char_p), ("model_par", c_double_p),
         ("n_model_par", C.c_int32), ("device", C.c_int32), ("prior_kind", c_int32_p), ("prior_par", c_double_p),
-        ("rank", C.c_int32), ("world_size", C.c_int32), ("nccl_unique_id", C.c_void_p), ("flags", C.c_uint32),
+        ("rank", C.c_int32), ("world_size", C.c_int32), ("nccl_unique_id", C.c_void_p), ("flags", C.c_uint32), ("ecdf_max_knots", C.c_int32),
     ]
 
 

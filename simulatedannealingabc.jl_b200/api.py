@@ -31,7 +31,7 @@ class Engine:
 
     def __init__(self, model: DeviceModel, prior: Distribution, *, n_particles: int, algorithm: str, proposal: Proposal,
                  resample: int, v: float, delta: float, seed: int = 0x5ABC, device: int = -1, rank: int = 0,
-                 world_size: int = 1, nccl_unique_id: bytes | None = None, flags: int = 0):
+                 world_size: int = 1, nccl_unique_id: bytes | None = None, flags: int = 0, ecdf_max_knots: int = 0):
         comps = prior.components()
         if len(comps) != model.n_para:
             raise _lib.SABCError(-20, f"prior has {len(comps)} components but model '{model.name}' has {model.n_para} parameters")
@@ -58,6 +58,7 @@ class Engine:
         cfg.rank, cfg.world_size = rank, world_size
         cfg.nccl_unique_id = C.cast(self._uid, C.c_void_p) if self._uid is not None else None
         cfg.flags = flags
+        cfg.ecdf_max_knots = int(ecdf_max_knots)
         self._h = C.c_void_p()
         _lib.check(_lib.lib().sabc_create(C.byref(self._h), C.byref(cfg)))
         nl, off = C.c_int64(), C.c_int64()
@@ -286,7 +287,7 @@ def sabc(f_dist, prior: Distribution, *args, n_particles: int = 100, n_simulatio
          algorithm: str = "single_eps", proposal: Proposal | None = None, resample: int | None = None,
          v: float = 1.0, delta: float = 0.1, checkpoint_history: int = 1, show_progressbar: bool = False,
          show_checkpoint=math.inf, type: str | None = None, seed: int = 0x5ABC, device: int = -1, comm=None,
-         flags: int = 0, **kwargs) -> SABCresult:
+         flags: int = 0, ecdf_max_knots: int = 0, **kwargs) -> SABCresult:
     """sabc(f_dist, prior, args...; kw...)  -- src/SimulatedAnnealingABC.jl:451-492."""
     if "δ" in kwargs:
         delta = kwargs.pop("δ")
@@ -308,7 +309,8 @@ def sabc(f_dist, prior: Distribution, *args, n_particles: int = 100, n_simulatio
         resample = 2 * n_particles                                                    # :455
     rank, world, uid = _distributed_setup(comm)
     eng = Engine(f_dist, prior, n_particles=n_particles, algorithm=algorithm, proposal=proposal, resample=resample,
-                 v=v, delta=delta, seed=seed, device=device, rank=rank, world_size=world, nccl_unique_id=uid, flags=flags)
+                 v=v, delta=delta, seed=seed, device=device, rank=rank, world_size=world, nccl_unique_id=uid, flags=flags,
+                 ecdf_max_knots=ecdf_max_knots)
     eng.init()                                                                        # :470-473
     res = SABCresult(eng, algorithm)
     n_sim_remaining = n_simulation - res.state.n_simulation                           # :478

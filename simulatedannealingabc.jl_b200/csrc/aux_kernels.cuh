@@ -32,6 +32,17 @@ static __global__ void k_sample16(const double* in, int64_t cnt_out, double* out
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt_out + ECDF_PAD; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = i < cnt_out ? in[i * ECDF_FANOUT] : dinf();
 }
+// compressed ECDF: K rank-uniform quantiles x[floor(i (m-1)/(K-1))], i = 0..K-1, of the m sorted positive distances
+static __global__ void k_ecdf_subsample(const double* sorted_pos, int64_t m, int K, double* out /* K + 2 + ECDF_PAD */) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K + 2 + ECDF_PAD; i += gridDim.x * blockDim.x) {
+        double v;
+        if (i == 0) v = 0.0;
+        else if (i <= K) v = sorted_pos[((int64_t)(i - 1) * (m - 1)) / (int64_t)(K - 1)];
+        else if (i == K + 1) v = sorted_pos[m - 1] * 1.5;
+        else v = dinf();
+        out[i] = v;
+    }
+}
 static __global__ void k_fill_inf(double* p, int n) {
     if (threadIdx.x < n) p[threadIdx.x] = dinf();
 }

@@ -77,6 +77,7 @@ struct sabc_engine {
     int64_t resample = 0;
     uint64_t seed = 0;
     uint32_t flags = 0;
+    int ecdf_max_knots = 0;
     int device = 0, rank = 0, world = 1, n_sm = 148;
     const ModelVTable* model = nullptr;
     ModelPar mp{};
@@ -211,6 +212,17 @@ static int ecdf_build_column(sabc_engine* e, int j, const double* d_col, int64_t
     SABC_CUDA(cudaMemcpyAsync(&n_pos, cnt.p, sizeof n_pos, cudaMemcpyDeviceToHost, e->stream));
     SABC_CUDA(cudaStreamSynchronize(e->stream));
     if (n_pos == 0) return set_error(SABC_ERR_NO_POSITIVE, "build_cdf: statistic %d has no positive prior distance", j + 1);
+    if (e->ecdf_max_knots >= 2 && (int64_t)n_pos > e->ecdf_max_knots) {      // compressed mode: keep K quantiles only
+        const int K = e->ecdf_max_knots;
+        auto* small = new DevBuf<double>();
+        SABC_CUDA(small->alloc((size_t)K + 2 + ECDF_PAD));
+        k_ecdf_subsample<<<(K + 2 + ECDF_PAD + 255) / 256, 256, 0, e->stream>>>(knots->p + 1, (int64_t)n_pos, K, small->p);
+        SABC_CUDA(cudaGetLastError());
+        SABC_CUDA(cudaStreamSynchronize(e->stream));
+        e->ecdf_bufs.pop_back(); delete knots;                                // the full sorted sample is not kept
+        e->ecdf_bufs.push_back(small);
+        return ecdf_attach(e, j, small, (int64_t)K + 2, std::max(top_max_for(e->S), K + 2));
+    }
     k_ecdf_ends<<<1, 1, 0, e->stream>>>(knots->p, (int64_t)n_pos);
     SABC_CUDA(cudaGetLastError());
     return ecdf_attach(e, j, knots, (int64_t)n_pos + 2, top_max_for(e->S));
@@ -498,6 +510,9 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     if (n_local < 4) return set_error(SABC_ERR_INVALID, "need at least 4 particles per GPU (each half >= 2)");
     if (c->n_particles > 0xffffffffLL) return set_error(SABC_ERR_INVALID, "n_particles exceeds 2^32-1");
     if (c->resample <= 0) return set_error(SABC_ERR_INVALID, "resample must be positive");
+    if (c->ecdf_max_knots != 0 && (c->ecdf_max_knots < 2 || (int64_t)(c->ecdf_max_knots + 2) * c->n_stats * 8 > 200 * 1024))
+        return set_error(SABC_ERR_INVALID, "ecdf_max_knots must be 0 or in [2, %d] for %d statistics (the compressed tables live in shared memory)",
+                         (int)(200 * 1024 / 8 / c->n_stats - 2), c->n_stats);
 
     int ndev = 0;
     SABC_CUDA(cudaGetDeviceCount(&ndev));
@@ -513,6 +528,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     e->n_eps = c->algorithm == SABC_ALG_MULTI_EPS ? c->n_stats : 1;
     e->prop_par[0] = c->prop_par[0]; e->prop_par[1] = c->prop_par[1];
     e->v = c->v; e->delta = c->delta; e->resample = c->resample; e->seed = c->seed; e->flags = c->flags;
+    e->ecdf_max_knots = c->ecdf_max_knots;
     if (e->flags & SABC_FLAG_TIME_KERNELS) e->flags |= SABC_FLAG_NO_GRAPH;
     if (world > 1) e->flags |= SABC_FLAG_NO_GRAPH;
     e->split = model->heavy && !(e->flags & SABC_FLAG_FUSED);
@@ -652,6 +668,8 @@ int sabc_init(sabc_engine* e) {
     SABC_TRY(ecdf_finalize(e));
 
     // u = G(ρ) (:190-192) + exact Σu
+    if (e->smem_update > 48 * 1024)
+        SABC_CUDA(cudaFuncSetAttribute(k_transform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_update));
     k_transform<<<(int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), CHUNK, e->smem_update, e->stream>>>(e->pop, n, e->S, e->b_ecdf.p, ds);
     SABC_CUDA(cudaGetLastError());
     // first resampling (:197), ε_0 (:200-204), history record 0 (:180,207-208)

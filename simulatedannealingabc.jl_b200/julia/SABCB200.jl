@@ -19,7 +19,7 @@ struct SabcConfig
     prop_par::NTuple{2,Float64}; v::Float64; delta::Float64; resample::Int64; seed::UInt64
     model_name::Cstring; model_par::Ptr{Float64}; n_model_par::Int32; device::Int32
     prior_kind::Ptr{Int32}; prior_par::Ptr{Float64}
-    rank::Int32; world_size::Int32; nccl_unique_id::Ptr{Cvoid}; flags::UInt32
+    rank::Int32; world_size::Int32; nccl_unique_id::Ptr{Cvoid}; flags::UInt32; ecdf_max_knots::Int32
 end
 
 struct SABCDeviceError <: Exception
@@ -58,7 +58,7 @@ end
 destroy!(e::Engine) = (e.h != C_NULL && ccall((:sabc_destroy, libsabc), Cint, (Ptr{Cvoid},), e.h); e.h = C_NULL; nothing)
 
 function Engine(model::DeviceModel, prior::Distribution; n_particles, algorithm, proposal::Proposal, resample, v, δ,
-                seed=0x5ABC, device=-1)
+                seed=0x5ABC, device=-1, ecdf_max_knots=0)
     comps = prior_components(prior)
     length(comps) == model.n_para || error("prior has $(length(comps)) components, model $(model.name) has $(model.n_para) parameters")
     kinds = Int32[prior_kind(c) for c in comps]
@@ -69,7 +69,7 @@ function Engine(model::DeviceModel, prior::Distribution; n_particles, algorithm,
     GC.@preserve kinds ppar model begin
         cfg = SabcConfig(n_particles, model.n_para, model.n_stats, alg, pcode, ppars, v, δ, resample, seed,
                          Base.unsafe_convert(Cstring, model.name), pointer(model.par), length(model.par), device,
-                         pointer(kinds), pointer(ppar), 0, 1, C_NULL, 0)
+                         pointer(kinds), pointer(ppar), 0, 1, C_NULL, 0, ecdf_max_knots)
         check(ccall((:sabc_create, libsabc), Cint, (Ref{Ptr{Cvoid}}, Ref{SabcConfig}), h, cfg))
     end
     e = Engine(h[], model, n_particles, model.n_para, model.n_stats, algorithm == :multi_eps ? model.n_stats : 1)

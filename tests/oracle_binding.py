@@ -17,7 +17,8 @@ vp, i64, i32, u64, u32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_
 class OrcConfig(C.Structure):
     _fields_ = [("n_particles", i64), ("n_para", i32), ("n_stats", i32), ("algorithm", i32), ("proposal", i32),
                 ("prop_par", dbl * 2), ("v", dbl), ("delta", dbl), ("resample", i64), ("seed", u64), ("model_id", i32),
-                ("n_model_par", i32), ("model_par", C.POINTER(dbl)), ("prior_kind", C.POINTER(i32)), ("prior_par", C.POINTER(dbl))]
+                ("n_model_par", i32), ("model_par", C.POINTER(dbl)), ("prior_kind", C.POINTER(i32)), ("prior_par", C.POINTER(dbl)),
+                ("ecdf_max_knots", i32)]
 
 
 MODEL_IDS = {"gauss_mean": 0, "gauss_sample": 1, "logistic": 2, "sir_tauleap": 3, "sir_gillespie": 4}
@@ -88,7 +89,7 @@ class OracleError(RuntimeError):
 class OracleEngine:
     """Drives the C oracle with the same arguments as sabc_b200.Engine."""
 
-    def __init__(self, model, prior, *, n_particles, algorithm, proposal, resample, v, delta, seed=0x5ABC):
+    def __init__(self, model, prior, *, n_particles, algorithm, proposal, resample, v, delta, seed=0x5ABC, ecdf_max_knots=0):
         comps = prior.components()
         self.N, self.d, self.s = int(n_particles), model.n_para, model.n_stats
         self.n_eps = self.s if algorithm == "multi_eps" else 1
@@ -106,6 +107,7 @@ class OracleEngine:
         cfg.model_par = self._par.ctypes.data_as(C.POINTER(dbl))
         cfg.prior_kind = self._kind.ctypes.data_as(C.POINTER(i32))
         cfg.prior_par = self._ppar.ctypes.data_as(C.POINTER(dbl))
+        cfg.ecdf_max_knots = int(ecdf_max_knots)
         self._h = vp()
         self._check(lib().orc_create(C.byref(self._h), C.byref(cfg)))
         self.seconds = 0.0

@@ -94,6 +94,28 @@ def test_split_and_fused_kernels_agree(gpu, name, prop):
         run_pair(model, prior, 1500, 8, proposal=proposal, resample=1500, flags=flags)
 
 
+@pytest.mark.parametrize("name,K", [("gauss_mean", 64), ("gauss_mean", 2046), ("gauss_sample_d2s2", 500), ("sir_tauleap", 1000), ("logistic", 300)])
+def test_compressed_ecdf_mode(gpu, name, K):
+    """ecdf_max_knots = K: the table keeps K rank-uniform quantiles and lives in shared memory as a whole.  The oracle applies the
+    same subsampling rule, so trajectories stay bit-identical; against the full ECDF the transform differs by O(1/K)."""
+    model, prior = model_cases()[name]
+    N = 6000
+    kw = dict(n_particles=N, algorithm="single_eps", proposal=DE(model.n_para), resample=N, v=1.0, delta=0.1, ecdf_max_knots=K)
+    eng, orc = make_pair(model, prior, **kw)
+    eng.init(); orc.init()
+    for j in range(model.n_stats):
+        kn = eng.get_ecdf(j)
+        assert kn.size <= K + 2 and np.array_equal(kn, orc.get_ecdf(j))
+    assert eng.kernel_info()["smem_bytes"] == sum(eng.get_ecdf(j).size for j in range(model.n_stats)) * 8
+    eng.update(10 * N); orc.update(10 * N)
+    assert_same_state(eng, orc, "compressed ECDF")
+    full = sb.Engine(model, prior, **{**kw, "ecdf_max_knots": 0}); full.init()
+    kf = full.get_ecdf(0); kc = eng.get_ecdf(0)
+    x = np.quantile(kf[1:-1], np.linspace(0.01, 0.99, 200))
+    import helpers
+    assert np.abs(helpers.g_ecdf_transform(kf, x) - helpers.g_ecdf_transform(kc, x)).max() < 3.0 / min(K, kf.size)
+
+
 def test_checkpoint_history_striding(gpu):
     """history every k-th update plus a final record (:367-382)."""
     model, prior = model_cases()["gauss_mean"]
