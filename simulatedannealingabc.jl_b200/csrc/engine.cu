@@ -668,7 +668,7 @@ int sabc_init(sabc_engine* e) {
     SABC_TRY(ecdf_finalize(e));
 
     // u = G(ρ) (:190-192) + exact Σu
-    if (e->smem_update > 48 * 1024)
+    if (e->smem_update > 40 * 1024)
         SABC_CUDA(cudaFuncSetAttribute(k_transform, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_update));
     k_transform<<<(int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), CHUNK, e->smem_update, e->stream>>>(e->pop, n, e->S, e->b_ecdf.p, ds);
     SABC_CUDA(cudaGetLastError());

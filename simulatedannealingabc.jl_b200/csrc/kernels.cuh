@@ -578,7 +578,7 @@ struct ModelLaunchers {
     }
     template <int PROP>
     static cudaError_t upd(const UpdateArgs& a, int grid, size_t smem, cudaStream_t s) {
-        if (smem > 48 * 1024)
+        if (smem > 40 * 1024)
             cudaFuncSetAttribute(update_half_kernel<M, PROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         update_half_kernel<M, PROP><<<grid, CHUNK, smem, s>>>(a);
         return cudaGetLastError();
@@ -592,6 +592,11 @@ struct ModelLaunchers {
         }
     }
     static cudaError_t occupancy(int proposal, size_t smem, int* b) {
+        if (smem > 40 * 1024) {      // the opt-in must precede the query, which otherwise reports 0 resident CTAs
+            cudaFuncSetAttribute(update_half_kernel<M, PROP_DE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(update_half_kernel<M, PROP_STRETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(update_half_kernel<M, PROP_RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
         switch (proposal) {
             case PROP_DE: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, update_half_kernel<M, PROP_DE>, CHUNK, smem);
             case PROP_STRETCH: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, update_half_kernel<M, PROP_STRETCH>, CHUNK, smem);
@@ -609,12 +614,14 @@ struct ModelLaunchers {
         return cudaGetLastError();
     }
     static cudaError_t simacc(const UpdateArgs& a, const SplitScratch& w, int grid, size_t smem, cudaStream_t s) {
-        if (smem > 48 * 1024)
+        if (smem > 40 * 1024)
             cudaFuncSetAttribute(simulate_accept_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         simulate_accept_kernel<M><<<grid, CHUNK, smem, s>>>(a, w);
         return cudaGetLastError();
     }
     static cudaError_t simacc_occ(size_t smem, int* b) {
+        if (smem > 40 * 1024)
+            cudaFuncSetAttribute(simulate_accept_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(b, simulate_accept_kernel<M>, CHUNK, smem);
     }
     static cudaError_t simulate(const double* th, int64_t n, int64_t ld, const ModelPar& mp, uint64_t seed,
