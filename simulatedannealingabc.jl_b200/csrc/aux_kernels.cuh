@@ -49,7 +49,7 @@ static __global__ void k_fill_inf(double* p, int n) {
 
 // u = G(ρ) for every particle and statistic + exact Σu limbs
 static __global__ void __launch_bounds__(CHUNK) k_transform(PopView pop, int64_t n, int S, const EcdfStat* ecdf, DevState* ds) {
-    extern __shared__ double s_top[];
+    extern __shared__ __align__(128) double s_top[];
     __shared__ unsigned long long s_acc[2 * MAX_S];
     for (int k = threadIdx.x; k < 2 * S; k += CHUNK) s_acc[k] = 0ull;
     stage_ecdf_top(ecdf, S, s_top);
@@ -76,7 +76,7 @@ static __global__ void __launch_bounds__(CHUNK) k_transform(PopView pop, int64_t
 
 // standalone transform used by the parity hook (one statistic, u only)
 static __global__ void __launch_bounds__(CHUNK) k_transform1(const double* rho, int64_t m, const EcdfStat* ecdf, double* u) {
-    extern __shared__ double s_top[];
+    extern __shared__ __align__(128) double s_top[];
     stage_ecdf_top(ecdf, 1, s_top);
     for (int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x; i < m; i += (int64_t)gridDim.x * CHUNK)
         u[i] = ecdf_eval(ecdf[0], s_top, rho[i]);

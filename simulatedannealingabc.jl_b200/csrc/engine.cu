@@ -169,7 +169,7 @@ static int ecdf_attach(sabc_engine* e, int j, DevBuf<double>* knots, int64_t L, 
 
 static int ecdf_finalize(sabc_engine* e) {
     int off = 0;
-    for (int j = 0; j < e->S; ++j) { e->h_ecdf[j].top_off = off; off += (int)e->h_ecdf[j].cnt[e->h_ecdf[j].nlev - 1]; }
+    for (int j = 0; j < e->S; ++j) { e->h_ecdf[j].top_off = off; off += (int)((e->h_ecdf[j].cnt[e->h_ecdf[j].nlev - 1] + 1) & ~(int64_t)1); }   // even: 16-byte bulk copies
     e->top_doubles = off;
     SABC_CUDA(e->b_ecdf.ensure(MAX_S));
     SABC_CUDA(cudaMemcpyAsync(e->b_ecdf.p, e->h_ecdf, sizeof(EcdfStat) * e->S, cudaMemcpyHostToDevice, e->stream));

@@ -180,7 +180,7 @@ int sabc_ecdf_transform(const double* knots, int64_t L, const double* rho, int64
     SABC_TRY(upload(dr, rho, (size_t)m)); SABC_CUDA(du.alloc((size_t)m));
     HookEcdf h;
     SABC_TRY(h.attach(dk.p, L, 2048));
-    const size_t smem = (size_t)h.st.cnt[h.st.nlev - 1] * sizeof(double);
+    const size_t smem = (size_t)((h.st.cnt[h.st.nlev - 1] + 1) & ~(int64_t)1) * sizeof(double);
     k_transform1<<<grid_for(m), CHUNK, smem>>>(dr.p, m, h.d_st.p, du.p);
     SABC_CUDA(cudaGetLastError());
     return download(u_out, du, (size_t)m);

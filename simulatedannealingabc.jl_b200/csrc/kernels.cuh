@@ -214,7 +214,11 @@ struct InactiveGather {
     SABC_D double operator()(int c, int64_t i) const { return base[c * ld + i]; }
 };
 
+// Stage the top index level of every statistic in shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP): one
+// elected thread posts the expected byte count on an mbarrier and issues one bulk copy per statistic; every thread then
+// waits on the barrier's phase.  Sizes are rounded up to 16 bytes (levels carry +inf padding, offsets are even).
 SABC_D void stage_ecdf_top(const EcdfStat* ecdf, int S, double* s_top) {
+#if defined(SABC_NO_TMA)
     for (int j = 0; j < S; ++j) {
         const EcdfStat& e = ecdf[j];
         const int top = e.nlev - 1;
@@ -223,6 +227,33 @@ SABC_D void stage_ecdf_top(const EcdfStat* ecdf, int S, double* s_top) {
         for (int64_t i = threadIdx.x; i < e.cnt[top]; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+#else
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int j = 0; j < S; ++j) total += (uint32_t)(((ecdf[j].cnt[ecdf[j].nlev - 1] + 1) & ~(int64_t)1) * 8);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
+        for (int j = 0; j < S; ++j) {
+            const EcdfStat& e = ecdf[j];
+            const int top = e.nlev - 1;
+            const uint32_t bytes = (uint32_t)(((e.cnt[top] + 1) & ~(int64_t)1) * 8);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_top + e.top_off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(e.lev[top]), "r"(bytes), "r"(mbar) : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mbar) : "memory");
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -232,7 +263,7 @@ SABC_D void stage_ecdf_top(const EcdfStat* ecdf, int S, double* s_top) {
 template <class M, int PROP>
 __global__ void __launch_bounds__(CHUNK) update_half_kernel(const UpdateArgs a) {
     constexpr int D = M::D, S = M::S;
-    extern __shared__ double s_top[];
+    extern __shared__ __align__(128) double s_top[];
     __shared__ unsigned long long s_acc[2 * S + 1];
     __shared__ double s_w[S][8];
     __shared__ double s_chol[PROP == PROP_RW ? D * D : 1];
@@ -374,7 +405,7 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, cons
 template <class M>
 __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kernel(const UpdateArgs a, const SplitScratch w) {
     constexpr int D = M::D, S = M::S;
-    extern __shared__ double s_top[];
+    extern __shared__ __align__(128) double s_top[];
     stage_ecdf_top(a.ecdf, S, s_top);
     const int lane = threadIdx.x & 31;
     const uint64_t sweep = 2ull * (uint64_t)a.ds->t + (uint64_t)a.half;
