@@ -79,6 +79,7 @@ typedef struct sabc_config {
 #define SABC_FLAG_TIME_KERNELS  2u  /* record CUDA events around every update_half / simulate_accept launch (implies NO_GRAPH) */
 #define SABC_FLAG_NO_PIPELINE   8u  /* sabc_update_host: upload, update, download strictly one after the other */
 #define SABC_FLAG_SORT_WORK    16u  /* split path: bucket the work list by the model's similarity key (if it has one) */
+#define SABC_FLAG_GENERIC_TAIL 32u  /* never use the single-CTA tail kernel of small populations */
 #define SABC_FLAG_FUSED         4u  /* always use the fused update_half kernel, also for simulation-heavy models */
 
 /* timing of the last sabc_update(), measured with CUDA events on the engine's stream */

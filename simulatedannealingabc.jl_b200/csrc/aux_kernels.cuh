@@ -121,9 +121,7 @@ SABC_D void post1_decide(DevState* ds, int S, int64_t n_global, int64_t resample
     }
     ds->w_total = 0ull;
 }
-static __global__ void __launch_bounds__(CHUNK) k_post1(const Post1Args a) {
-    __shared__ double s_w[8];
-    const int b = blockIdx.x;
+SABC_D void d_post1_block(const Post1Args& a, int b, double* s_w) {
     if (b < 2 * a.S) {
         const int half = b / a.S, j = b % a.S;
         const double r = cta_treesum(a.rho_part + ((int64_t)half * a.S + j) * a.part_ld, half == 0 ? a.groups0 : a.groups1,
@@ -132,6 +130,10 @@ static __global__ void __launch_bounds__(CHUNK) k_post1(const Post1Args a) {
     } else if (a.decide && threadIdx.x == 0) {
         post1_decide(a.ds, a.S, a.n_global, a.resample);
     }
+}
+static __global__ void __launch_bounds__(CHUNK) k_post1(const Post1Args a) {
+    __shared__ double s_w[8];
+    d_post1_block(a, blockIdx.x, s_w);
 }
 static __global__ void k_decide(DevState* ds, int S, int64_t n_global, int64_t resample) {
     if (threadIdx.x == 0) post1_decide(ds, S, n_global, resample);
@@ -164,15 +166,12 @@ SABC_D unsigned long long cta_sum_u64(unsigned long long v, unsigned long long* 
 }
 
 // w_i = exp(-Σ_j u_ij δ / ū_j) as 32.32 fixed point, plus per-tile sums  (:127)
-static __global__ void __launch_bounds__(CHUNK) k_weights(PopView pop, int64_t n, int S, double delta, const DevState* ds,
-                                                   unsigned long long* q, unsigned long long* tile_sum, int force) {
-    if (!force && !ds->resample_flag) return;
-    __shared__ unsigned long long s8[8];
-    __shared__ double s_ubar[MAX_S];
+SABC_D void d_weights(const PopView& pop, int64_t n, int S, double delta, const DevState* ds, unsigned long long* q,
+                      unsigned long long* tile_sum, int vb, int vg, unsigned long long* s8, double* s_ubar) {
     if (threadIdx.x < S) s_ubar[threadIdx.x] = ds->ubar[threadIdx.x];
     __syncthreads();
     const int64_t n_tiles = (n + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = vb; tile < n_tiles; tile += vg) {
         const int64_t base = tile * TILE + (int64_t)threadIdx.x * 8;
         unsigned long long local = 0;
         for (int k = 0; k < 8; ++k) {
@@ -190,6 +189,13 @@ static __global__ void __launch_bounds__(CHUNK) k_weights(PopView pop, int64_t n
         const unsigned long long tot = cta_sum_u64(local, s8);
         if (threadIdx.x == 0) tile_sum[tile] = tot;
     }
+}
+static __global__ void __launch_bounds__(CHUNK) k_weights(PopView pop, int64_t n, int S, double delta, const DevState* ds,
+                                                   unsigned long long* q, unsigned long long* tile_sum, int force) {
+    if (!force && !ds->resample_flag) return;
+    __shared__ unsigned long long s8[8];
+    __shared__ double s_ubar[MAX_S];
+    d_weights(pop, n, S, delta, ds, q, tile_sum, blockIdx.x, gridDim.x, s8, s_ubar);
 }
 // standalone per-tile sums of an existing integer array (multi-GPU selection flags, hooks)
 static __global__ void __launch_bounds__(CHUNK) k_tile_sums(const unsigned long long* q, int64_t n, unsigned long long* tile_sum) {
@@ -243,13 +249,10 @@ static __global__ void __launch_bounds__(1024) k_scan_tiles(const unsigned long 
     if (threadIdx.x == 0) *total_out = s_carry;
 }
 // inclusive prefix sums in place: q[i] <- tile_off + Σ_{k<=i in tile} q[k]
-static __global__ void __launch_bounds__(CHUNK) k_prefix(unsigned long long* q, int64_t n, const unsigned long long* tile_off,
-                                                  const DevState* ds, int force) {
-    if (!force && !ds->resample_flag) return;
-    __shared__ unsigned long long s_warp[8];
+SABC_D void d_prefix(unsigned long long* q, int64_t n, const unsigned long long* tile_off, int vb, int vg, unsigned long long* s_warp) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t n_tiles = (n + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = vb; tile < n_tiles; tile += vg) {
         const int64_t base = tile * TILE + (int64_t)threadIdx.x * 8;
         unsigned long long v[8], run = 0;
         for (int k = 0; k < 8; ++k) { v[k] = base + k < n ? q[base + k] : 0ull; run += v[k]; v[k] = run; }
@@ -268,6 +271,12 @@ static __global__ void __launch_bounds__(CHUNK) k_prefix(unsigned long long* q, 
         __syncthreads();
     }
 }
+static __global__ void __launch_bounds__(CHUNK) k_prefix(unsigned long long* q, int64_t n, const unsigned long long* tile_off,
+                                                  const DevState* ds, int force) {
+    if (!force && !ds->resample_flag) return;
+    __shared__ unsigned long long s_warp[8];
+    d_prefix(q, n, tile_off, blockIdx.x, gridDim.x, s_warp);
+}
 
 // first index i in [0,n) with P[i] > r
 SABC_HD int64_t upper_bound_u64(const unsigned long long* P, int64_t n, unsigned long long r) {
@@ -281,16 +290,14 @@ SABC_HD int64_t upper_bound_u64(const unsigned long long* P, int64_t n, unsigned
 
 // N iid categorical draws by inversion of the exact prefix sums, fused with the gather of
 // population[idx] and u[idx,:] (:129-132; ρ is not resampled, :197,341) and the exact Σu of the result.
-static __global__ void __launch_bounds__(CHUNK) k_draw_gather(PopView pop, PopView tmp, int64_t n, int D, int S,
-                                                       const unsigned long long* P, uint64_t seed, DevState* ds, int force) {
-    if (!force && !ds->resample_flag) return;
-    __shared__ unsigned long long s_acc[2 * MAX_S];
+SABC_D void d_draw_gather(const PopView& pop, const PopView& tmp, int64_t n, int D, int S, const unsigned long long* P, uint64_t seed,
+                          DevState* ds, int vb, int vg, unsigned long long* s_acc) {
     for (int k = threadIdx.x; k < 2 * S; k += CHUNK) s_acc[k] = 0ull;
     __syncthreads();
     const unsigned long long W = ds->w_total;
     const uint32_t rc = (uint32_t)ds->n_resampling;
     const int64_t n_groups = (n + CHUNK - 1) / CHUNK;
-    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    for (int64_t grp = vb; grp < n_groups; grp += vg) {
         const int64_t k = grp * CHUNK + threadIdx.x;
         int64_t src = 0;
         if (k < n) {
@@ -318,13 +325,22 @@ static __global__ void __launch_bounds__(CHUNK) k_draw_gather(PopView pop, PopVi
         atomicAdd(&ds->r_lo[threadIdx.x], s_acc[2 * threadIdx.x + 1]);
     }
 }
-static __global__ void k_copyback(PopView pop, PopView tmp, int64_t n, int D, int S, const DevState* ds, int force) {
+static __global__ void __launch_bounds__(CHUNK) k_draw_gather(PopView pop, PopView tmp, int64_t n, int D, int S,
+                                                       const unsigned long long* P, uint64_t seed, DevState* ds, int force) {
     if (!force && !ds->resample_flag) return;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    __shared__ unsigned long long s_acc[2 * MAX_S];
+    d_draw_gather(pop, tmp, n, D, S, P, seed, ds, blockIdx.x, gridDim.x, s_acc);
+}
+SABC_D void d_copyback(const PopView& pop, const PopView& tmp, int64_t n, int D, int S, int64_t first, int64_t stride) {
+    for (int64_t i = first; i < n; i += stride) {
         for (int c = 0; c < D; ++c) pop.theta[c * pop.ld + i] = tmp.theta[c * tmp.ld + i];
         for (int j = 0; j < S; ++j) pop.u[j * pop.ld + i] = tmp.u[j * tmp.ld + i];
         pop.lp[i] = tmp.lp[i];
     }
+}
+static __global__ void k_copyback(PopView pop, PopView tmp, int64_t n, int D, int S, const DevState* ds, int force) {
+    if (!force && !ds->resample_flag) return;
+    d_copyback(pop, tmp, n, D, S, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 // indices only (parity hook)
 static __global__ void k_draw_indices(const unsigned long long* P, int64_t n, unsigned long long W, uint64_t seed, uint32_t rc,
@@ -345,9 +361,7 @@ struct FinishArgs {
     int64_t n_global;
     double v;
 };
-static __global__ void k_finish(const FinishArgs a) {
-    __shared__ double s_um[MAX_S];
-    __shared__ unsigned long long s_hi[MAX_S], s_lo[MAX_S];
+SABC_D void d_finish(const FinishArgs& a, double* s_um, unsigned long long* s_hi, unsigned long long* s_lo) {
     DevState* ds = a.ds;
     const int tid = threadIdx.x;
     const int flag = ds->resample_flag;
@@ -387,6 +401,48 @@ static __global__ void k_finish(const FinishArgs a) {
         for (int k = 0; k < MAX_SLOTS; ++k) { ds->list_count[k] = 0u; ds->list_cursor[k] = 0u; }
         ds->t += 1; ds->ix += 1;
     }
+}
+static __global__ void k_finish(const FinishArgs a) {
+    __shared__ double s_um[MAX_S];
+    __shared__ unsigned long long s_hi[MAX_S], s_lo[MAX_S];
+    d_finish(a, s_um, s_hi, s_lo);
+}
+
+// ---- small populations: everything after the two half-sweeps in ONE single-CTA kernel (rho tree sums, trigger, resampling,
+// eps, history).  For n <= 16384 the nine tiny launches of the generic tail cost more than their work; results are identical.
+struct TailArgs {
+    Post1Args post;
+    FinishArgs fin;
+    PopView pop, tmp;
+    int64_t n; int D, S;
+    double delta; uint64_t seed;
+    unsigned long long *q, *tile_sum, *tile_off;
+};
+static __global__ void __launch_bounds__(CHUNK) k_tail_small(const TailArgs a) {
+    __shared__ double s_w[8];
+    __shared__ unsigned long long s8[8], s_acc[2 * MAX_S], s_hi[MAX_S], s_lo[MAX_S];
+    __shared__ double s_ubar[MAX_S], s_um[MAX_S];
+    DevState* ds = a.post.ds;
+    for (int b = 0; b <= 2 * a.S; ++b) d_post1_block(a.post, b, s_w);
+    __syncthreads();
+    if (ds->resample_flag) {
+        d_weights(a.pop, a.n, a.S, a.delta, ds, a.q, a.tile_sum, 0, 1, s8, s_ubar);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long run = 0;
+            const int64_t n_tiles = (a.n + TILE - 1) / TILE;
+            for (int64_t t = 0; t < n_tiles; ++t) { a.tile_off[t] = run; run += a.tile_sum[t]; }
+            ds->w_total = run;
+        }
+        __syncthreads();
+        d_prefix(a.q, a.n, a.tile_off, 0, 1, s8);
+        __syncthreads();
+        d_draw_gather(a.pop, a.tmp, a.n, a.D, a.S, a.q, a.seed, ds, 0, 1, s_acc);
+        __syncthreads();
+        d_copyback(a.pop, a.tmp, a.n, a.D, a.S, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    d_finish(a.fin, s_um, s_hi, s_lo);
 }
 
 // ---- RandomWalk covariance (update_proposal!, src/proposals.jl:46-48,58-60) ----

@@ -355,7 +355,10 @@ static int launch_finish(sabc_engine* e) {
     return 0;
 }
 
-static int kernels_per_iteration(const sabc_engine* e) { return (e->split ? 6 : 2) + (e->sort_work ? 6 : 0) + 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1; }
+static bool small_tail(const sabc_engine* e);
+static int kernels_per_iteration(const sabc_engine* e) {
+    return (e->split ? 6 : 2) + (e->sort_work ? 6 : 0) + (small_tail(e) ? 1 : 1 + 5 + (e->proposal == PROP_RW ? 6 : 0) + 1);
+}
 
 // the two half-sweeps (:304-332) in the fused or the split form.  A pipelined host call cuts each half into sub-ranges
 // (identical results: the particles of a half-sweep are independent) so that transfers overlap at a finer grain.
@@ -380,8 +383,29 @@ static int enqueue_sweeps(sabc_engine* e) {
 
 // one population update, single GPU: every launch is unconditional, the resampling kernels
 // return immediately unless the device-side trigger fired
+static bool small_tail(const sabc_engine* e) { return !(e->flags & SABC_FLAG_GENERIC_TAIL) && e->world == 1 && e->proposal != PROP_RW && e->n_local <= 16384; }
+
+static int launch_tail_small(sabc_engine* e) {
+    TailArgs a{};
+    Post1Args& p = a.post;
+    p.ds = e->b_ds.p; p.rho_part = e->b_rho_part.p; p.part_ld = e->part_ld;
+    int64_t o, n0, n1, t0, t1;
+    halves(e, 0, o, n0, t0, t1); halves(e, 1, o, n1, t0, t1);
+    p.groups0 = (n0 + CHUNK - 1) / CHUNK; p.groups1 = (n1 + CHUNK - 1) / CHUNK;
+    p.scratch = e->b_scratch.p; p.scratch_ld = e->scratch_ld;
+    p.S = e->S; p.n_global = e->N; p.resample = e->resample; p.decide = 1;
+    FinishArgs& f = a.fin;
+    f.ds = e->b_ds.p; f.hist = e->b_hist.p; f.S = e->S; f.n_eps = e->n_eps; f.algorithm = e->algorithm; f.n_global = e->N; f.v = e->v;
+    a.pop = e->pop; a.tmp = e->tmp; a.n = e->n_local; a.D = e->D; a.S = e->S; a.delta = e->delta; a.seed = e->seed;
+    a.q = e->b_q.p; a.tile_sum = e->b_tile_sum.p; a.tile_off = e->b_tile_off.p;
+    k_tail_small<<<1, CHUNK, 0, e->stream>>>(a);
+    SABC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int enqueue_iteration(sabc_engine* e) {
     SABC_TRY(enqueue_sweeps(e));
+    if (small_tail(e)) return launch_tail_small(e);
     SABC_TRY(launch_post1(e, 1));
     SABC_TRY(launch_resample_local(e, 0));
     SABC_TRY(launch_update_proposal(e));
@@ -417,7 +441,13 @@ static int append_history(sabc_engine* e, int64_t n_rec) {
 
 static int ensure_hist(sabc_engine* e, int64_t n_rec) {
     const int w = e->n_eps + 2 * e->S;
-    if (n_rec > e->hist_cap) { SABC_CUDA(e->b_hist.alloc((size_t)n_rec * w)); e->hist_cap = n_rec; }
+    if (n_rec > e->hist_cap) {
+        const int64_t cap = std::max<int64_t>(n_rec, 1024);
+        SABC_CUDA(e->b_hist.alloc((size_t)cap * w));
+        e->hist_cap = cap;
+        // the captured graph holds the old buffer address in its kernel arguments
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    }
     return 0;
 }
 

@@ -116,6 +116,18 @@ def test_compressed_ecdf_mode(gpu, name, K):
     assert np.abs(helpers.g_ecdf_transform(kf, x) - helpers.g_ecdf_transform(kc, x)).max() < 3.0 / min(K, kf.size)
 
 
+@pytest.mark.parametrize("name", ["gauss_mean", "gauss_sample_d2s2", "sir_tauleap"])
+@pytest.mark.parametrize("n", [100, 2049, 16384])
+def test_small_population_tail_kernel(gpu, name, n):
+    """n <= 16384: one single-CTA kernel replaces the generic tail (rho sums, trigger, resampling, eps, history); both forms and
+    the oracle must agree bit for bit, including iterations that resample."""
+    model, prior = model_cases()[name]
+    alg = "multi_eps" if name == "gauss_sample_d2s2" else "single_eps"
+    for flags in (0, sb.SABC_FLAG_GENERIC_TAIL, sb.SABC_FLAG_NO_GRAPH):
+        eng, orc = run_pair(model, prior, n, 12, algorithm=alg, resample=max(4, n // 3), flags=flags)
+        assert eng.get_state()[1][2] >= 3
+
+
 def test_checkpoint_history_striding(gpu):
     """history every k-th update plus a final record (:367-382)."""
     model, prior = model_cases()["gauss_mean"]
@@ -137,6 +149,20 @@ def test_resume_matches_single_run(gpu):
     before = b.get_state()[1].copy(); nh = b.get_history()[0].shape[0]
     b.update(50)
     assert np.array_equal(b.get_state()[1], before) and b.get_history()[0].shape[0] == nh
+
+
+def test_growing_update_calls_keep_history(gpu):
+    """update calls of growing length re-allocate the device history buffer; the replayed CUDA graph must not keep the old
+    address (regression: found by bench.py --graph --steps 200 after a 3-step warm-up)."""
+    model, prior = model_cases()["gauss_sample_d2s2"]
+    kw = dict(n_particles=20_000, algorithm="multi_eps", proposal=DE(2), resample=20_000, v=1.0, delta=0.1)
+    eng, orc = make_pair(model, prior, **kw)
+    eng.init(); orc.init()
+    for n_upd in (3, 40, 1500):
+        eng.update(n_upd * 20_000); orc.update(n_upd * 20_000)
+    assert_same_state(eng, orc, "growing calls")
+    for a, b in zip(eng.get_history(), orc.get_history()):
+        assert a.shape == b.shape and np.array_equal(a, b)
 
 
 def test_host_round_trip(gpu):
