@@ -111,6 +111,29 @@ class ClockSampler:
                 "power_w_max": pmax or None, "reasons": sorted(reasons), "samples": len(rows), "samples_under_load": len(loaded)}
 
 
+def pin_to_gpu_numa_node(index: int) -> str:
+    """Bind this process (and the pinned host buffers it allocates afterwards) to the NUMA node of GPU `index`: with one
+    process per GPU the e2e copies otherwise cross the socket interconnect for half of the GPUs."""
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True,
+                             text=True, timeout=10).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus                      # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"node {node} ({len(cpus)} cpus)"
+        return "no allowed cpu on the node"
+    except Exception as ex:                                              # plumbing only: never fail the run
+        return f"not pinned ({type(ex).__name__})"
+
+
 def measured_peak_hbm() -> tuple[float, str]:
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
@@ -124,6 +147,7 @@ def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, ste
     uses Threads.@threads) on a bounded sample of the workload.  Returns (updates/s, cores, description, ms_per_step)."""
     import oracle_binding as ob
     import sabc_b200 as sb
+    ob.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))      # torchrun exports OMP_NUM_THREADS=1: use every host thread we may run on
     cores = ob.lib().orc_num_threads()
     kw = dict(algorithm=algorithm, proposal=sb.DifferentialEvolution(n_para=model.n_para), v=1.0, delta=0.1)
     n_cal = min(max_particles, max(256 * cores, 20000))
@@ -193,6 +217,7 @@ def main():
 
     # ------------------------------------------------------------------ B200 arm
     dist = None
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else "single process, not pinned"
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -314,6 +339,7 @@ def main():
                    "proposal": "DifferentialEvolution", "resample": 2 * N, "checkpoint_history": 1, "ecdf_max_knots": args.ecdf_knots,
                    "rng": "Philox4x32-10 counter streams", "accept_fraction": accept_frac,
                    "l2": f"per-GPU working set {(8 * nl * (d + 2 * s + 1) + 8 * s * (N + 2)) / 1e6:.0f} MB (state + ECDF tables) vs 126 MB L2; no explicit flush",
+                   "host_numa": numa,
                    "launch": "direct launches with event pairs" if time_kernels_live else ("host-driven + NCCL" if world > 1 else "CUDA graph replay")},
         "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,

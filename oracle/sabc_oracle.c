@@ -24,6 +24,13 @@ static _Thread_local char g_err[512];
 const char* orc_last_error(void) { return g_err; }
 static int fail(int code, const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); return code; }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -94,6 +94,7 @@ int  orc_get_history(orc_engine* e, double* eps_h, double* u_h, double* rho_h);
 int64_t orc_get_ecdf(orc_engine* e, int32_t stat, double* knots_out);
 int  orc_set_ecdf(orc_engine* e, int32_t stat, const double* knots, int64_t L);
 int  orc_num_threads(void);
+void orc_set_num_threads(int n);   /* launchers such as torchrun export OMP_NUM_THREADS=1 */
 const char* orc_last_error(void);
 
 #ifdef __cplusplus

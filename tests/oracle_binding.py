@@ -68,7 +68,7 @@ def lib() -> C.CDLL:
             "orc_get_population": (C.c_int, [vp, vp, vp, vp]), "orc_set_population": (C.c_int, [vp, vp, vp, vp, vp, vp]),
             "orc_get_state": (C.c_int, [vp, vp, vp]), "orc_history_len": (i64, [vp]), "orc_get_history": (C.c_int, [vp, vp, vp, vp]),
             "orc_get_ecdf": (i64, [vp, i32, vp]), "orc_set_ecdf": (C.c_int, [vp, i32, vp, i64]),
-            "orc_num_threads": (C.c_int, []), "orc_last_error": (C.c_char_p, []),
+            "orc_num_threads": (C.c_int, []), "orc_set_num_threads": (None, [C.c_int]), "orc_last_error": (C.c_char_p, []),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n); f.restype = r; f.argtypes = a
