@@ -202,7 +202,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        val, cores, sample, ms = cpu_oracle_throughput(model, prior, algorithm, target_seconds=60.0, steps=args.steps,
+        val, cores, sample, ms = cpu_oracle_throughput(model, prior, algorithm, target_seconds=float(os.environ.get("SABC_BENCH_REF_SECONDS", "60")), steps=args.steps,
                                                        warmup=args.warmup, max_particles=n_per_gpu * max(world, args.gpus))
         line = {"impl": "reference", "metric": "particle-sim-updates/sec", "value": val, "unit": "particle-updates/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
