@@ -80,6 +80,8 @@ typedef struct sabc_config {
 #define SABC_FLAG_NO_PIPELINE   8u  /* sabc_update_host: upload, update, download strictly one after the other */
 #define SABC_FLAG_SORT_WORK    16u  /* split path: bucket the work list by the model's similarity key (if it has one) */
 #define SABC_FLAG_GENERIC_TAIL 32u  /* never use the single-CTA tail kernel of small populations */
+#define SABC_FLAG_MG_REPLICATED 64u /* world_size > 1: every rank holds the whole population and simulates a share of each half-sweep;
+                                       bit-identical to one GPU (strict mode for parity studies, memory does not scale) */
 #define SABC_FLAG_FUSED         4u  /* always use the fused update_half kernel, also for simulation-heavy models */
 
 /* timing of the last sabc_update(), measured with CUDA events on the engine's stream */

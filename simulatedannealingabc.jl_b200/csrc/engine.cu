@@ -79,6 +79,8 @@ struct sabc_engine {
     uint32_t flags = 0;
     int ecdf_max_knots = 0;
     int device = 0, rank = 0, world = 1, n_sm = 148;
+    bool replicated = false;   // world > 1 with the whole population on every GPU (SABC_FLAG_MG_REPLICATED)
+    bool sharded() const { return world > 1 && !replicated; }
     const ModelVTable* model = nullptr;
     ModelPar mp{};
     PriorSpec prior{};
@@ -383,7 +385,7 @@ static int enqueue_sweeps(sabc_engine* e) {
 
 // one population update, single GPU: every launch is unconditional, the resampling kernels
 // return immediately unless the device-side trigger fired
-static bool small_tail(const sabc_engine* e) { return !(e->flags & SABC_FLAG_GENERIC_TAIL) && e->world == 1 && e->proposal != PROP_RW && e->n_local <= 16384; }
+static bool small_tail(const sabc_engine* e) { return !(e->flags & SABC_FLAG_GENERIC_TAIL) && !e->sharded() && e->proposal != PROP_RW && e->n_local <= 16384; }
 
 static int launch_tail_small(sabc_engine* e) {
     TailArgs a{};
@@ -554,6 +556,11 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     auto* e = new sabc_engine();
     e->N = c->n_particles; e->n_local = n_local; e->rank = world > 1 ? c->rank : 0; e->world = world;
     e->offset = (int64_t)e->rank * n_local;
+    e->replicated = world > 1 && (c->flags & SABC_FLAG_MG_REPLICATED);
+    if (e->replicated) {
+        if (world > MAX_SUB) { delete e; return set_error(SABC_ERR_INVALID, "replicated mode supports at most %d ranks", MAX_SUB); }
+        e->n_local = c->n_particles; e->offset = 0;          // every rank holds the whole population and simulates a share
+    }
     e->D = c->n_para; e->S = c->n_stats; e->algorithm = c->algorithm; e->proposal = c->proposal;
     e->n_eps = c->algorithm == SABC_ALG_MULTI_EPS ? c->n_stats : 1;
     e->prop_par[0] = c->prop_par[0]; e->prop_par[1] = c->prop_par[1];
@@ -580,7 +587,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     e->n_sm = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(set_error(SABC_ERR_CUDA, "stream creation failed"));
 
-    const size_t n = (size_t)n_local;
+    const size_t n = (size_t)e->n_local;
     cudaError_t ce = cudaSuccess;
     auto A = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
     A(e->b_theta.alloc(n * e->D)); A(e->b_u.alloc(n * e->S)); A(e->b_rho.alloc(n * e->S)); A(e->b_lp.alloc(n));
@@ -610,6 +617,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
         if (rc == 0) rc = mg_warm_p2p(e);
         if (rc) return fail(rc);
         // work space of the global resampling, allocated once (a cudaMalloc inside the update loop costs tens of ms)
+        if (e->replicated) { *out = e; return 0; }
         const size_t Ng = (size_t)e->N, Nt = (Ng + TILE - 1) / TILE;
         cudaError_t ce2 = e->mg.F.alloc(Ng);
         if (ce2 == cudaSuccess) ce2 = e->mg.src.alloc(Ng);
@@ -672,12 +680,12 @@ int sabc_init(sabc_engine* e) {
     k_treesum_cols<<<e->S, CHUNK, 0, e->stream>>>(e->b_rho_part.p, e->part_ld, groups, e->b_scratch.p, e->scratch_ld,
                                                   &ds->rho_sum[0][0]);
     SABC_CUDA(cudaGetLastError());
-    if (e->world > 1) SABC_TRY(mg_allreduce_f64(e, &ds->rho_sum[0][0], e->S));
+    if (e->sharded()) SABC_TRY(mg_allreduce_f64(e, &ds->rho_sum[0][0], e->S));
     {
         int err = 0;
         SABC_CUDA(cudaMemcpyAsync(&err, &ds->error_flag, sizeof err, cudaMemcpyDeviceToHost, e->stream));
         SABC_CUDA(cudaStreamSynchronize(e->stream));
-        if (e->world > 1) SABC_TRY(mg_any_flag(e, &err));
+        if (e->sharded()) SABC_TRY(mg_any_flag(e, &err));
         if (err & 1) return set_error(SABC_ERR_NEG_DISTANCE, "Negative distances are not allowed!");
     }
 
@@ -688,10 +696,10 @@ int sabc_init(sabc_engine* e) {
         DevBuf<unsigned char> cub_tmp;
         DevBuf<unsigned long long> cnt;
         SABC_CUDA(keys.alloc((size_t)e->N)); SABC_CUDA(cnt.alloc(1));
-        if (e->world > 1) SABC_CUDA(gathered.alloc((size_t)e->N));
+        if (e->sharded()) SABC_CUDA(gathered.alloc((size_t)e->N));
         for (int j = 0; j < e->S; ++j) {
             const double* col = e->pop.rho + (int64_t)j * e->pop.ld;
-            if (e->world > 1) { SABC_TRY(mg_allgather_f64(e, col, gathered.p, n)); col = gathered.p; }
+            if (e->sharded()) { SABC_TRY(mg_allgather_f64(e, col, gathered.p, n)); col = gathered.p; }
             SABC_TRY(ecdf_build_column(e, j, col, e->N, keys, cub_tmp, cnt));
         }
     }
@@ -703,10 +711,10 @@ int sabc_init(sabc_engine* e) {
     k_transform<<<(int)std::min<int64_t>(groups, (int64_t)e->n_sm * 8), CHUNK, e->smem_update, e->stream>>>(e->pop, n, e->S, e->b_ecdf.p, ds);
     SABC_CUDA(cudaGetLastError());
     // first resampling (:197), ε_0 (:200-204), history record 0 (:180,207-208)
-    if (e->world > 1) SABC_TRY(mg_reduce_iteration_sums(e));
+    if (e->sharded()) SABC_TRY(mg_reduce_iteration_sums(e));
     k_decide<<<1, 32, 0, e->stream>>>(ds, e->S, e->N, e->resample);          // ū for the weights
     SABC_CUDA(cudaGetLastError());
-    if (e->world > 1) SABC_TRY(mg_resample(e)); else SABC_TRY(launch_resample_local(e, 1));
+    if (e->sharded()) SABC_TRY(mg_resample(e)); else SABC_TRY(launch_resample_local(e, 1));
     k_force_flag<<<1, 1, 0, e->stream>>>(ds, 1);
     SABC_TRY(launch_finish(e));
     int64_t n_rec = 0;
@@ -735,7 +743,7 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
     SABC_TRY(ensure_hist(e, n_pop / checkpoint_history + 2));
     k_begin<<<1, 1, 0, e->stream>>>(ds, (long long)(e->n_population_updates + 1), (long long)n_pop, (long long)checkpoint_history);
     SABC_CUDA(cudaGetLastError());
-    if (e->world > 1) SABC_TRY(launch_update_proposal_mg(e)); else SABC_TRY(launch_update_proposal(e));   // :284
+    if (e->sharded()) SABC_TRY(launch_update_proposal_mg(e)); else SABC_TRY(launch_update_proposal(e));   // :284
 
     cudaEvent_t ev0, ev1;
     SABC_CUDA(cudaEventCreate(&ev0)); SABC_CUDA(cudaEventCreate(&ev1));
@@ -748,7 +756,7 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
         if (time_kernels) e->kev = &kev;
         for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) {
             e->pipe_first = piped && ix == 0; e->pipe_last = piped && ix == n_pop - 1;
-            rc = mg_iteration(e);
+            rc = e->replicated ? rep_iteration(e) : mg_iteration(e);
         }
         e->kev = nullptr; e->pipe_first = e->pipe_last = false;
         SABC_CUDA(cudaEventRecord(ev1, e->stream));
@@ -848,7 +856,7 @@ int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, doub
     if (!theta || !u || !rho || !eps || !counters) return set_error(SABC_ERR_INVALID, "null argument");
     SABC_CUDA(cudaSetDevice(e->device));
     const int64_t n = e->n_local, h0 = n / 2, n_pop = n_simulation / e->N;
-    const bool pipe = n_pop >= 1 && n >= 32768 && !(e->flags & SABC_FLAG_NO_PIPELINE) && e->top_doubles > 0 &&
+    const bool pipe = n_pop >= 1 && n >= 32768 && !(e->flags & SABC_FLAG_NO_PIPELINE) && !e->replicated && e->top_doubles > 0 &&
                       e->v > 0.0 && e->delta > 0.0;
     cudaEvent_t a, b, c, d;
     SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b)); SABC_CUDA(cudaEventCreate(&c)); SABC_CUDA(cudaEventCreate(&d));

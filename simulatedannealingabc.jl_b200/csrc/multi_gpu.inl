@@ -196,3 +196,49 @@ static int mg_iteration(sabc_engine* e) {
     SABC_TRY(launch_finish(e));
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Replicated multi-GPU mode (SABC_FLAG_MG_REPLICATED): every rank keeps the WHOLE population and simulates a contiguous
+// share of each half-sweep; the updated rows are broadcast after the sweep and everything else (statistics, resampling,
+// eps) runs replicated.  Halves, partners and slots are those of the single-GPU algorithm, so the result is bit-identical
+// to one GPU and to the oracle -- the "strict" mode of SURVEY.md section 8e, used for parity studies (memory does not scale).
+// ------------------------------------------------------------------------------------------------
+static __global__ void k_zero_u_sums(DevState* ds) {
+    if (threadIdx.x < MAX_S) { ds->u_hi[threadIdx.x] = 0ull; ds->u_lo[threadIdx.x] = 0ull; }
+}
+static int rep_iteration(sabc_engine* e) {
+    NcclApi* nc = nccl_api();
+    DevState* ds = e->b_ds.p;
+    const int G = e->world;
+    for (int half = 0; half < 2; ++half) {
+        if (e->split) { SABC_TRY(launch_split_propose(e, half, e->rank, G)); SABC_TRY(launch_split_simacc(e, half, e->rank, G)); }
+        else SABC_TRY(launch_update_half(e, half, e->rank, G));
+        int64_t off, an, t0, t1;
+        halves(e, half, off, an, t0, t1);
+        SABC_NCCL(nc->GroupStart());
+        for (int g = 0; g < G; ++g) {
+            int64_t r0, r1;
+            sub_range(an, g, G, r0, r1);
+            if (r1 <= r0) continue;
+            const size_t cnt = (size_t)(r1 - r0);
+            for (int c = 0; c < e->D; ++c) { double* p = e->pop.theta + (int64_t)c * e->pop.ld + off + r0; SABC_NCCL(nc->Broadcast(p, p, cnt, ncclFloat64, g, e->comm.comm, e->stream)); }
+            for (int j = 0; j < e->S; ++j) {
+                double* pu = e->pop.u + (int64_t)j * e->pop.ld + off + r0; SABC_NCCL(nc->Broadcast(pu, pu, cnt, ncclFloat64, g, e->comm.comm, e->stream));
+                double* pr = e->pop.rho + (int64_t)j * e->pop.ld + off + r0; SABC_NCCL(nc->Broadcast(pr, pr, cnt, ncclFloat64, g, e->comm.comm, e->stream));
+            }
+            double* pl = e->pop.lp + off + r0; SABC_NCCL(nc->Broadcast(pl, pl, cnt, ncclFloat64, g, e->comm.comm, e->stream));
+        }
+        SABC_NCCL(nc->GroupEnd());
+    }
+    // accept count of all shares; statistics over the replicated arrays (the sweeps only saw a share)
+    SABC_TRY(mg_allreduce_u64(e, &ds->n_acc_iter, 1));
+    k_zero_u_sums<<<1, 32, 0, e->stream>>>(ds);
+    SABC_CUDA(cudaGetLastError());
+    SABC_TRY(launch_split_stats(e));
+    if (small_tail(e)) return launch_tail_small(e);
+    SABC_TRY(launch_post1(e, 1));
+    SABC_TRY(launch_resample_local(e, 0));
+    SABC_TRY(launch_update_proposal(e));
+    SABC_TRY(launch_finish(e));
+    return 0;
+}

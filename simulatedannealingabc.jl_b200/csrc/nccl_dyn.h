@@ -15,6 +15,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -33,11 +34,11 @@ inline NcclApi* nccl_api() {
 #define SABC_SYM(field, sym) api.field = (decltype(api.field))dlsym(api.handle, sym)
             SABC_SYM(GetUniqueId, "ncclGetUniqueId"); SABC_SYM(CommInitRank, "ncclCommInitRank");
             SABC_SYM(CommDestroy, "ncclCommDestroy"); SABC_SYM(AllReduce, "ncclAllReduce");
-            SABC_SYM(AllGather, "ncclAllGather"); SABC_SYM(Send, "ncclSend"); SABC_SYM(Recv, "ncclRecv");
+            SABC_SYM(AllGather, "ncclAllGather"); SABC_SYM(Broadcast, "ncclBroadcast"); SABC_SYM(Send, "ncclSend"); SABC_SYM(Recv, "ncclRecv");
             SABC_SYM(GroupStart, "ncclGroupStart"); SABC_SYM(GroupEnd, "ncclGroupEnd");
             SABC_SYM(GetErrorString, "ncclGetErrorString");
 #undef SABC_SYM
-            if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather || !api.Send || !api.Recv ||
+            if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather || !api.Broadcast || !api.Send || !api.Recv ||
                 !api.GroupStart || !api.GroupEnd) { dlclose(api.handle); api.handle = nullptr; }
         }
     }

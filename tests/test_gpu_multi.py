@@ -66,6 +66,28 @@ for name, N, n_upd, prop in (("gauss_mean", 4000 * world, 30, "de"), ("gauss_sam
     report[name + "_" + prop] = {"eps": eps.tolist(), "counters": cnt.tolist(), "mean_u": all_u.mean(axis=0).tolist()}
     eng.close()
 
+# replicated ("strict") mode: whole population on every rank, each simulates a share -> bit-identical to the oracle
+import oracle_binding as ob
+for name, N, n_upd, prop, alg in (("gauss_mean", 3000, 25, "de", "single_eps"), ("sir_tauleap", 2500, 10, "stretch", "single_eps"),
+                                  ("gauss_sample_d2s2", 20000, 12, "rw", "multi_eps"), ("logistic", 1111 * world, 8, "de", "single_eps")):
+    model, prior = model_cases()[name]
+    proposal = {"de": sb.DifferentialEvolution(n_para=model.n_para), "stretch": sb.StretchMove(), "rw": sb.RandomWalk(n_para=model.n_para)}[prop]
+    N = (N // world) * world
+    kw = dict(n_particles=N, algorithm=alg, proposal=proposal, resample=N // 2, v=1.0, delta=0.1)
+    comm = new_comm()
+    eng = sb.Engine(model, prior, device=int(os.environ["LOCAL_RANK"]), rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2],
+                    flags=sb.SABC_FLAG_MG_REPLICATED, **kw)
+    assert eng.n_local == N and eng.offset == 0
+    eng.init(); eng.update(n_upd * N)
+    orc = ob.OracleEngine(model, prior, **kw); orc.init(); orc.update(n_upd * N)
+    for nm, a, b in zip(("theta", "u", "rho"), eng.get_population(), orc.get_population()):
+        assert np.array_equal(a, b), (name, nm, int((a != b).sum()))
+    assert np.array_equal(eng.get_state()[0], orc.get_state()[0]) and np.array_equal(eng.get_state()[1], orc.get_state()[1])
+    for a, b in zip(eng.get_history(), orc.get_history()):
+        assert np.array_equal(a, b)
+    assert eng.get_state()[1][2] >= 2
+    eng.close()
+
 # resampling alone: run one forced global resampling through init on a tiny problem and check it copies existing particles
 model, prior = model_cases()["gauss_sample_d2s2"]
 N = 1024 * world
