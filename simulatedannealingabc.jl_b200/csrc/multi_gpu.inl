@@ -201,7 +201,7 @@ static int mg_iteration(sabc_engine* e) {
 // Replicated multi-GPU mode (SABC_FLAG_MG_REPLICATED): every rank keeps the WHOLE population and simulates a contiguous
 // share of each half-sweep; the updated rows are broadcast after the sweep and everything else (statistics, resampling,
 // eps) runs replicated.  Halves, partners and slots are those of the single-GPU algorithm, so the result is bit-identical
-// to one GPU and to the oracle -- the "strict" mode of SURVEY.md section 8e, used for parity studies (memory does not scale).
+// to one GPU -- the "strict" mode of SURVEY.md section 8e, used for parity studies (memory does not scale).
 // ------------------------------------------------------------------------------------------------
 static __global__ void k_zero_u_sums(DevState* ds) {
     if (threadIdx.x < MAX_S) { ds->u_hi[threadIdx.x] = 0ull; ds->u_lo[threadIdx.x] = 0ull; }

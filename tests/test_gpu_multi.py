@@ -73,7 +73,7 @@ for name, N, n_upd, prop, alg in (("gauss_mean", 3000, 25, "de", "single_eps"), 
     model, prior = model_cases()[name]
     proposal = {"de": sb.DifferentialEvolution(n_para=model.n_para), "stretch": sb.StretchMove(), "rw": sb.RandomWalk(n_para=model.n_para)}[prop]
     N = (N // world) * world
-    kw = dict(n_particles=N, algorithm=alg, proposal=proposal, resample=N // 2, v=1.0, delta=0.1)
+    kw = dict(n_particles=N, algorithm=alg, proposal=proposal, resample=N // 8, v=1.0, delta=0.1)
     comm = new_comm()
     eng = sb.Engine(model, prior, device=int(os.environ["LOCAL_RANK"]), rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2],
                     flags=sb.SABC_FLAG_MG_REPLICATED, **kw)
@@ -159,7 +159,9 @@ def test_sharded_population(gpu, world, tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), str(script)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    if r.returncode != 0:
+        lines = [l for l in (r.stdout + r.stderr).splitlines() if any(k in l for k in ("Error", "assert", "Traceback", "File \"/", "rank"))]
+        raise AssertionError("\n".join(lines[-40:]))
     assert r.stdout.count("OK") == world
     rep = [l for l in r.stdout.splitlines() if l.startswith("REPORT ")]
     assert rep and json.loads(rep[0][7:])
