@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsabc_b200.so")
+# SABC_B200_LIB: development override to load an experimental build of the same CUDA library (tools/, A/B timing)
+LIB_PATH = os.environ.get("SABC_B200_LIB") or os.path.join(HERE, "libsabc_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)

@@ -9,7 +9,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libsabc_b200.so")
+# SABC_LIB_OUT / SABC_EXTRA_NVCC_FLAGS: development knobs for building an experimental variant next to the product
+# library (objects then go to a variant-specific directory); the product build uses neither.
+LIB = os.environ.get("SABC_LIB_OUT") or os.path.join(HERE, "libsabc_b200.so")
+EXTRA = os.environ.get("SABC_EXTRA_NVCC_FLAGS", "").split()
+OBJDIR = CSRC if not os.environ.get("SABC_LIB_OUT") else LIB + ".obj"
 SOURCES = ["engine.cu", "hooks.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -41,10 +45,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        os.makedirs(OBJDIR, exist_ok=True)
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         if not force and _newer(obj, deps):
             return obj
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *EXTRA, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -100,6 +100,51 @@ SABC_HD double rcp_int(int k) {
 #endif
 }
 
+// ln(y) for a positive normal y with |error| <= 2e-9: exponent split, mantissa moved to [sqrt(1/2), sqrt(2)), then a
+// degree-10 polynomial in t = m - 1 (Chebyshev interpolant of ln(1+t)/t; measured maximum error 1.62e-9).  No division:
+// about a third of det_log's instructions.  NOT part of the numerical specification -- it only feeds ptrs_filter().
+SABC_HD double approx_log(double y) {
+    uint64_t b = f64_bits(y);
+    uint32_t top = (uint32_t)(b >> 32);
+    int k = (int)(top >> 20) - 1023;
+    top &= 0x000fffffu;
+    const uint32_t bump = (top + 0x95f64u) & 0x100000u;
+    k += (int)(bump >> 20);
+    b = ((uint64_t)(top | (bump ^ 0x3ff00000u)) << 32) | (b & 0xffffffffULL);
+    const double t = bits_f64(b) - 1.0;
+    double q = -0x1.313359b9a714ep-4;
+    q = dfma(q, t, 0x1.0647858f47021p-3);  q = dfma(q, t, -0x1.0fb035e36d8d6p-3);
+    q = dfma(q, t, 0x1.22cf0fbed0be2p-3);  q = dfma(q, t, -0x1.5423b015df288p-3);
+    q = dfma(q, t, 0x1.999e867edab4ap-3);  q = dfma(q, t, -0x1.000423b72b7d5p-2);
+    q = dfma(q, t, 0x1.55555d65bf746p-2);  q = dfma(q, t, -0x1.fffff847a7034p-2);
+    q = dfma(q, t, 0x1.fffffffab3c37p-1);
+    return dfma((double)k, 0x1.62e42fefa39efp-1, t * q);
+}
+
+// Cheap decision of the exact PTRS acceptance test  log(num/den) <= -lam + k log(lam) - log(k!)  (the last lines of
+// poisson_attempt).  With x = k+1 and Stirling's series for log Gamma(x) the difference rhs - lhs is
+//   T = (x - lam) - log(sqrt(2 pi)) - [1/(12x) - 1/(360x^3) + 1/(1260x^5)] - k (ln x - ln lam) - ln(x)/2 - ln(num) + ln(den),
+// which approx_log evaluates to within (2k + 2.5) * 1.62e-9 + 1/(1680 x^7) + rounding; the spec'd test itself carries
+// about 1e-15 * k * ln(lam) of rounding.  Returns +1 (the exact test accepts) or -1 (it rejects) when |T| exceeds a bound
+// E = 1e-6 + 5e-9 k that covers all of these with margin, 0 (undecided: run the exact test) otherwise.  About one slow-path
+// attempt in 10^3..10^4 is undecided, so warps almost never execute the three det_log + det_logfact of the exact test;
+// the decisions -- and therefore every Poisson draw -- are unchanged (tools/check_ptrs_filter.cpp compares them on
+// >10^9 attempts on the CPU; the GPU parity tests compare the draws with the oracle, which has no filter).
+SABC_HD int ptrs_filter(double lam, double kf, double num, double den) {
+    if (!(kf >= 2.0) || !(kf < 1e12) || !(num > 0x1p-1000) || !(den > 0x1p-1000) || !(den < 0x1p1000)) return 0;
+    const double x = kf + 1.0;
+    const double lx = approx_log(x), ll = approx_log(lam);
+    const double rx = drcp(x), rx2 = rx * rx;
+    const double corr = rx * dfma(-rx2, dfma(-rx2, 1.0 / 1260.0, 1.0 / 360.0), 1.0 / 12.0);
+    double T = (x - lam) - 0x1.d67f1c864beb5p-1;
+    T = T - corr;
+    T = dfma(-kf, lx - ll, T);
+    T = dfma(-0.5, lx, T);
+    T = T - (approx_log(num) - approx_log(den));
+    const double E = dfma(kf, 5e-9, 1e-6);
+    return T > E ? 1 : (T < -E ? -1 : 0);
+}
+
 // Poisson(lam): one-uniform sequential-search inversion below 10, Hoermann's PTRS (1993) above, with
 // the acceptance tests rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one Philox
 // block (none when lam <= 0) and either returns a count or rejects; this is the unit the SIR kernel interleaves
@@ -111,6 +156,12 @@ SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
         const double U = u53(w.a);
         double p = det_exp(-lam), F = p;
         int k = 0;
+#if defined(__CUDA_ARCH__)
+        // same arithmetic as the loop below while the 1/k table covers k (lam < 10: in practice always); no branch on k
+        // inside, so a trip is 8 instructions instead of 17
+#pragma unroll 4
+        while (U > F && k < 63) { k++; p = (p * lam) * c_rcp_int[k]; F = F + p; }
+#endif
         while (U > F && k < 1024) { k++; p = (p * lam) * rcp_int(k); F = F + p; }         // p_k = p_{k-1} λ (1/k)
         k_out = k;
         return true;
@@ -127,6 +178,13 @@ SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
     const double bm = b - 3.4;
     const double num = V * (1.1239 * bm + 1.1328);
     const double den = bm * ((a * r) * r + b);
+#if !defined(SABC_NO_PTRS_FILTER)
+    const int dec = ptrs_filter(lam, kf, num, den);
+#if defined(SABC_FILTER_STAT)
+    SABC_FILTER_STAT(dec);
+#endif
+    if (dec != 0) { k_out = (int64_t)kf; return dec > 0; }
+#endif
     const double lhs = det_log(num / den);
     const double rhs = (-lam + kf * det_log(lam)) - det_logfact(kf);
     if (lhs <= rhs) { k_out = (int64_t)kf; return true; }

@@ -291,10 +291,13 @@ struct Logistic {
     }
 };
 
+#ifndef SABC_SIR_MIN_BLOCKS
+#define SABC_SIR_MIN_BLOCKS 4
+#endif
 // C4: SIR tau-leap, θ = (β, γ, ι, φ).  par: pop, T, tau, obs_total, obs_peak, obs_tpeak
 struct SirTauLeap {
     static constexpr int D = 4, S = 3;
-    static constexpr int SIM_MIN_BLOCKS = 4;   // cap at 64 registers: 32 warps per SM hide the FP64 latencies
+    static constexpr int SIM_MIN_BLOCKS = SABC_SIR_MIN_BLOCKS;   // 4: cap at 64 registers, 32 warps per SM hide the FP64 latencies
     // similarity key of a proposal for the work-list bucketing: growth rate β−γ (6 bits), initial fraction ι (3), γ (3).
     // Particles of one bucket have similar epidemic curves, so the lanes of a warp meet the same sampler regimes and
     // finish together.  The key only orders the work; it never enters the arithmetic.
