@@ -158,6 +158,11 @@ int  sabc_treesum(const double* x, int64_t n, double* sum_out);
 int  sabc_detmath(int32_t op, const double* x, int64_t n, double* out);
 int  sabc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int  sabc_poisson(const double* lam, int64_t n, uint64_t seed, uint64_t sweep, int64_t* k_out, uint32_t* blocks_out);
+/* the two cheap filters in front of the exact PTRS acceptance test (csrc/philox.cuh) against that test on `attempts`
+ * candidates, lambda cycling through lam[]: counts_out = {reached the exact test, undecided by the MUFU filter, undecided
+ * by both, wrong decisions of the MUFU filter, wrong decisions of the FP64 filter}; ratio_out = max |T - T_exact| / E */
+int  sabc_ptrs_filter_check(const double* lam, int32_t n_lam, int64_t attempts, uint64_t seed, int64_t counts_out[5],
+                            double ratio_out[2]);
 int  sabc_prior_logpdf(int32_t d, const int32_t* kind, const double* par, const double* theta /* n x d */, int64_t n,
                        double* lp_out);
 /* f_dist on the device: theta is n x d column-major, rho_out n x s; particle i uses Philox counter particle_base+i */

@@ -89,6 +89,7 @@ SYMBOLS = {
     "sabc_detmath": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "sabc_philox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sabc_poisson": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "sabc_ptrs_filter_check": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "sabc_prior_logpdf": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "sabc_model_simulate": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p]),
     "sabc_model_info": (C.c_int, [C.c_char_p, c_int32_p, c_int32_p]),

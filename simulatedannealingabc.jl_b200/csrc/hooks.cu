@@ -5,6 +5,7 @@
 #include "common.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 using namespace sabc;
@@ -47,6 +48,31 @@ __global__ void k_poisson(const double* lam, int64_t n, uint64_t seed, uint64_t 
         k_out[i] = poisson(lam[i], st);
         blocks[i] = st.next;
     }
+}
+// statistics of the two PTRS acceptance filters against the exact test (philox.cuh), over `attempts` candidates
+__global__ void k_ptrs_filter_check(const double* lam, int n_lam, int64_t attempts, uint64_t seed, unsigned long long* counts,
+                                    unsigned long long* ratio_bits) {
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    double r1 = 0.0, r2 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < attempts; i += (int64_t)gridDim.x * blockDim.x) {
+        const double l = lam[i % n_lam];
+        Stream st(seed, (uint32_t)i, (uint64_t)(i >> 32), KIND_MODEL);
+        double kf, num = 0.0, den = 0.0;
+        if (ptrs_candidate(l, st.draw(), kf, num, den) != 2) continue;
+        const bool ex = ptrs_exact(l, kf, num, den);
+        const double Tex = ((-l + kf * det_log(l)) - det_logfact(kf)) - det_log(num / den);
+        float T1, E1; double T2, E2;
+        const int d1 = ptrs_filter_mufu(l, kf, num, den, T1, E1);
+        const int d2 = ptrs_filter(l, kf, num, den, T2, E2);
+        c[0]++;
+        c[1] += d1 == 0; c[2] += d1 == 0 && d2 == 0;
+        c[3] += d1 != 0 && (d1 > 0) != ex; c[4] += d2 != 0 && (d2 > 0) != ex;
+        if (E1 > 0.0f) { const double r = fabs((double)T1 - Tex) / (double)E1; if (r > r1) r1 = r; }
+        if (E2 > 0.0) { const double r = fabs(T2 - Tex) / E2; if (r > r2) r2 = r; }
+    }
+    for (int j = 0; j < 5; ++j) if (c[j]) atomicAdd(counts + j, c[j]);
+    atomicMax(ratio_bits + 0, (unsigned long long)__double_as_longlong(r1));   // non-negative doubles order like integers
+    atomicMax(ratio_bits + 1, (unsigned long long)__double_as_longlong(r2));
 }
 __global__ void k_accept(int64_t m, int s, const double* uo, const double* un, const double* eps, int n_eps, const double* dlp,
                          const double* lf, const double* U, uint8_t* acc) {
@@ -145,6 +171,21 @@ int sabc_poisson(const double* lam, int64_t n, uint64_t seed, uint64_t sweep, in
     SABC_CUDA(cudaGetLastError());
     SABC_TRY(download(k_out, dk, (size_t)n));
     if (blocks_out) SABC_TRY(download(blocks_out, db, (size_t)n));
+    return 0;
+}
+
+int sabc_ptrs_filter_check(const double* lam, int32_t n_lam, int64_t attempts, uint64_t seed, int64_t counts_out[5],
+                           double ratio_out[2]) {
+    if (!lam || n_lam < 1 || attempts < 0 || !counts_out || !ratio_out) return set_error(SABC_ERR_INVALID, "bad argument");
+    DevBuf<double> dl; DevBuf<unsigned long long> dc;
+    SABC_TRY(upload(dl, lam, (size_t)n_lam)); SABC_CUDA(dc.alloc(7));
+    SABC_CUDA(cudaMemset(dc.p, 0, 7 * sizeof(unsigned long long)));
+    k_ptrs_filter_check<<<148 * 8, 256>>>(dl.p, n_lam, attempts, seed, dc.p, dc.p + 5);
+    SABC_CUDA(cudaGetLastError());
+    unsigned long long h[7];
+    SABC_TRY(download(h, dc, 7));
+    for (int j = 0; j < 5; ++j) counts_out[j] = (int64_t)h[j];
+    for (int j = 0; j < 2; ++j) { double r; memcpy(&r, &h[5 + j], 8); ratio_out[j] = r; }
     return 0;
 }
 

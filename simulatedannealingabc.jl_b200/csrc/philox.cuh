@@ -121,34 +121,97 @@ SABC_HD double approx_log(double y) {
     return dfma((double)k, 0x1.62e42fefa39efp-1, t * q);
 }
 
-// Cheap decision of the exact PTRS acceptance test  log(num/den) <= -lam + k log(lam) - log(k!)  (the last lines of
-// poisson_attempt).  With x = k+1 and Stirling's series for log Gamma(x) the difference rhs - lhs is
+// Cheap decision of the exact PTRS acceptance test  log(num/den) <= -lam + k log(lam) - log(k!)  (ptrs_exact below).
+// With x = k+1 and Stirling's series for log Gamma(x) the difference rhs - lhs is
 //   T = (x - lam) - log(sqrt(2 pi)) - [1/(12x) - 1/(360x^3) + 1/(1260x^5)] - k (ln x - ln lam) - ln(x)/2 - ln(num) + ln(den),
 // which approx_log evaluates to within (2k + 2.5) * 1.62e-9 + 1/(1680 x^7) + rounding; the spec'd test itself carries
 // about 1e-15 * k * ln(lam) of rounding.  Returns +1 (the exact test accepts) or -1 (it rejects) when |T| exceeds a bound
 // E = 1e-6 + 5e-9 k that covers all of these with margin, 0 (undecided: run the exact test) otherwise.  About one slow-path
 // attempt in 10^3..10^4 is undecided, so warps almost never execute the three det_log + det_logfact of the exact test;
 // the decisions -- and therefore every Poisson draw -- are unchanged (tools/check_ptrs_filter.cpp compares them on
-// >10^9 attempts on the CPU; the GPU parity tests compare the draws with the oracle, which has no filter).
-SABC_HD int ptrs_filter(double lam, double kf, double num, double den) {
+// >10^9 attempts on the CPU; the GPU parity tests compare the draws with the CPU restatement, which has no filter).
+SABC_HD int ptrs_filter(double lam, double kf, double num, double den, double& T, double& E) {
+    T = 0.0; E = 0.0;
     if (!(kf >= 2.0) || !(kf < 1e12) || !(num > 0x1p-1000) || !(den > 0x1p-1000) || !(den < 0x1p1000)) return 0;
     const double x = kf + 1.0;
     const double lx = approx_log(x), ll = approx_log(lam);
     const double rx = drcp(x), rx2 = rx * rx;
     const double corr = rx * dfma(-rx2, dfma(-rx2, 1.0 / 1260.0, 1.0 / 360.0), 1.0 / 12.0);
-    double T = (x - lam) - 0x1.d67f1c864beb5p-1;
+    T = (x - lam) - 0x1.d67f1c864beb5p-1;
     T = T - corr;
     T = dfma(-kf, lx - ll, T);
     T = dfma(-0.5, lx, T);
     T = T - (approx_log(num) - approx_log(den));
-    const double E = dfma(kf, 5e-9, 1e-6);
+    E = dfma(kf, 5e-9, 1e-6);
     return T > E ? 1 : (T < -E ? -1 : 0);
 }
+SABC_HD int ptrs_filter(double lam, double kf, double num, double den) {
+    double T, E; return ptrs_filter(lam, kf, num, den, T, E);
+}
 
-// Poisson(lam): one-uniform sequential-search inversion below 10, Hoermann's PTRS (1993) above, with
-// the acceptance tests rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one Philox
-// block (none when lam <= 0) and either returns a count or rejects; this is the unit the SIR kernel interleaves
-// across lanes so that a rejection in one lane does not stall the accepted lanes of its warp.
+#if defined(__CUDACC__)
+// log2 on the special-function unit: ONE MUFU.LG2 (arguments here are normal floats, so the flush-to-zero form needs no
+// pre-scaling).  Documented accuracy of lg2.approx: absolute error <= 2^-21.41 on [0.5, 2], <= 2 ulp elsewhere.
+SABC_D float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+SABC_D float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// First-level filter, device only: the same T in single precision with the logarithms on the MUFU unit -- about 35
+// instructions against ~180 of ptrs_filter and ~330 of the exact test.  The k ln(x/lam) term is taken as k ln(1 + D/lam)
+// with D = x - lam exact in FP64, so its error is k times that of ONE logarithm near 1:
+//   MUFU 2^-21.41 ln2 = 2.5e-7, the argument (three roundings and a 1-ulp reciprocal) <= 3.6e-7 on [0.5, 2]  ->  6.1e-7 k
+//   (q in (2, 256]: 2 ulp of |log2 q| <= 8 plus the argument: 1.5e-6 k); the FP32 products and sums of the two large
+//   terms, each at most 2|D| on q <= 2: < 4.1e-7 |D|; everything else (ln x / 2, ln num - ln den with |log2| < 128,
+//   Stirling truncated after 1/(360 x^3) with x >= 3) < 5e-5.
+// Bound used: E = 2e-4 + k (q <= 2 ? 1e-6 : 3e-6) + 5e-7 |D|.  Outside the guarded ranges, or when |T| <= E, it returns 0 and the
+// FP64 filter above decides (or passes on to the exact test).  A NaN anywhere fails both comparisons and falls through.
+// tests/test_gpu_hooks.py::test_ptrs_filters_agree_with_exact_test checks decisions and the margin |T - T_exact| / E on the GPU.
+SABC_D int ptrs_filter_mufu(double lam, double kf, double num, double den, float& T, float& E) {
+    T = 0.0f; E = 0.0f;
+    if (!(kf >= 2.0) || !(kf < 1e7) || !(num > 0x1p-100) || !(den > 0x1p-100) || !(den < 0x1p100)) return 0;
+    const double x = kf + 1.0;
+    const double D = x - lam;
+    const float xf = __double2float_rn(x), kff = __double2float_rn(kf);
+    const float q = __fadd_rn(1.0f, __fmul_rn(__double2float_rn(D), mufu_rcp(__double2float_rn(lam))));
+    if (!(q >= 0.5f) || !(q <= 256.0f)) return 0;
+    const float rx = mufu_rcp(xf);
+    const float corr = __fmul_rn(rx, __fmaf_rn(__fmul_rn(rx, rx), -1.0f / 360.0f, 1.0f / 12.0f));
+    // ln2 * [ k log2 q + log2(x)/2 + log2 num - log2 den ]
+    float L = __fmaf_rn(kff, mufu_lg2(q), __fmul_rn(0.5f, mufu_lg2(xf)));
+    L = __fadd_rn(L, __fsub_rn(mufu_lg2(__double2float_rn(num)), mufu_lg2(__double2float_rn(den))));
+    const float Df = __double2float_rn(D - 0x1.d67f1c864beb5p-1);
+    T = __fsub_rn(__fsub_rn(Df, corr), __fmul_rn(0.693147180559945f, L));
+    E = __fmaf_rn(kff, q <= 2.0f ? 1e-6f : 3e-6f, __fmaf_rn(fabsf(Df), 5e-7f, 2e-4f));
+    return T > E ? 1 : (T < -E ? -1 : 0);
+}
+#endif
+
+// Hoermann's PTRS (1993) for lam >= 10, split into the candidate with its cheap tests and the exact test.
+// ptrs_candidate: 1 = accept kf, 0 = reject, 2 = the exact test on (kf, num, den) decides.
+SABC_HD int ptrs_candidate(double lam, const U64x2 w, double& kf, double& num, double& den) {
+    const double slam = sqrt(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double U = u53(w.a) - 0.5, V = u53(w.b);
+    const double us = 0.5 - fabs(U);
+    const double r = drcp(us);
+    kf = floor(((2.0 * a) * r + b) * U + lam + 0.43);
+    if (us >= 0.07 && (0.9277 - V) * (b - 2.0) >= 3.6224) return 1;
+    if (kf < 0.0 || (us < 0.013 && V > us)) return 0;
+    const double bm = b - 3.4;
+    num = V * (1.1239 * bm + 1.1328);
+    den = bm * ((a * r) * r + b);
+    return 2;
+}
+SABC_HD bool ptrs_exact(double lam, double kf, double num, double den) {
+    const double lhs = det_log(num / den);
+    const double rhs = (-lam + kf * det_log(lam)) - det_logfact(kf);
+    return lhs <= rhs;
+}
+
+// Poisson(lam): one-uniform sequential-search inversion below 10, PTRS above, with the acceptance tests
+// rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one Philox block (none when
+// lam <= 0) and either returns a count or rejects; this is the unit the SIR kernel interleaves across lanes so that a
+// rejection in one lane does not stall the accepted lanes of its warp.  The two filters only shortcut the exact test.
 SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
     if (!(lam > 0.0)) { k_out = 0; return true; }
     const U64x2 w = st.draw();
@@ -157,8 +220,7 @@ SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
         double p = det_exp(-lam), F = p;
         int k = 0;
 #if defined(__CUDA_ARCH__)
-        // same arithmetic as the loop below while the 1/k table covers k (lam < 10: in practice always); no branch on k
-        // inside, so a trip is 8 instructions instead of 17
+        // same arithmetic as the loop below while the 1/k table covers k (lam < 10: in practice always); no branch on k inside
 #pragma unroll 4
         while (U > F && k < 63) { k++; p = (p * lam) * c_rcp_int[k]; F = F + p; }
 #endif
@@ -166,29 +228,26 @@ SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
         k_out = k;
         return true;
     }
-    const double slam = sqrt(lam);
-    const double b = 0.931 + 2.53 * slam;
-    const double a = -0.059 + 0.02483 * b;
-    const double U = u53(w.a) - 0.5, V = u53(w.b);
-    const double us = 0.5 - fabs(U);
-    const double r = drcp(us);
-    const double kf = floor(((2.0 * a) * r + b) * U + lam + 0.43);
-    if (us >= 0.07 && (0.9277 - V) * (b - 2.0) >= 3.6224) { k_out = (int64_t)kf; return true; }
-    if (kf < 0.0 || (us < 0.013 && V > us)) return false;
-    const double bm = b - 3.4;
-    const double num = V * (1.1239 * bm + 1.1328);
-    const double den = bm * ((a * r) * r + b);
+    double kf, num = 0.0, den = 0.0;
+    int s = ptrs_candidate(lam, w, kf, num, den);
+    if (s == 2) {
 #if !defined(SABC_NO_PTRS_FILTER)
-    const int dec = ptrs_filter(lam, kf, num, den);
+        int dec = 0;
+#if defined(__CUDA_ARCH__) && !defined(SABC_NO_MUFU_FILTER)
+        { float T1, E1; dec = ptrs_filter_mufu(lam, kf, num, den, T1, E1); }
+        if (dec == 0)
+#endif
+            dec = ptrs_filter(lam, kf, num, den);
 #if defined(SABC_FILTER_STAT)
-    SABC_FILTER_STAT(dec);
+        SABC_FILTER_STAT(dec);
 #endif
-    if (dec != 0) { k_out = (int64_t)kf; return dec > 0; }
+        s = dec != 0 ? (dec > 0) : (int)ptrs_exact(lam, kf, num, den);
+#else
+        s = (int)ptrs_exact(lam, kf, num, den);
 #endif
-    const double lhs = det_log(num / den);
-    const double rhs = (-lam + kf * det_log(lam)) - det_logfact(kf);
-    if (lhs <= rhs) { k_out = (int64_t)kf; return true; }
-    return false;
+    }
+    if (s == 1) k_out = (int64_t)kf;
+    return s == 1;
 }
 SABC_HD int64_t poisson(double lam, Stream& st) {
     int64_t k;

@@ -51,6 +51,26 @@ def test_poisson_bit_exact(gpu):
     assert abs((k[big] / lam[big]).mean() - 1) < 0.01
 
 
+def test_ptrs_filters_agree_with_exact_test(gpu):
+    """The two cheap filters in front of the exact PTRS acceptance test (csrc/philox.cuh) may only shortcut it: on 4e9
+    candidates over lambda in [10, 1e7] neither takes a decision the exact test does not take, their error stays well
+    inside the bound they use, and they leave only a small share of the candidates to the exact test."""
+    rng = np.random.default_rng(11)
+    lam = np.concatenate([10 ** rng.uniform(1, 7, 4000), rng.uniform(10, 40, 1000), [10.0, 10.5, 16.0, 17.0, 1e5, 25000.0]])
+    counts = np.zeros(5, dtype=np.int64); ratio = np.zeros(2)
+    L.check(L.lib().sabc_ptrs_filter_check(ptr(lam), lam.size, 4_000_000_000, C.c_uint64(99), ptr(counts), ptr(ratio)))
+    slow, und1, und12, bad1, bad2 = (int(c) for c in counts)
+    print("ptrs filters:", dict(reached=slow, undecided_mufu=und1, undecided_both=und12, bad_mufu=bad1, bad_fp64=bad2), ratio)
+    assert slow > 5e8 and bad1 == 0 and bad2 == 0
+    assert ratio[0] < 0.7 and ratio[1] < 0.7, ratio          # measured error / bound used
+    # typical C4 rates (lambda 30 .. 3e4): nearly every candidate is decided by the first filter
+    lam = 10 ** rng.uniform(1.5, 4.5, 4000)
+    L.check(L.lib().sabc_ptrs_filter_check(ptr(lam), lam.size, 400_000_000, C.c_uint64(100), ptr(counts), ptr(ratio)))
+    print("ptrs filters, C4 range:", counts, ratio)
+    assert counts[3] == 0 and counts[4] == 0
+    assert counts[1] < 0.05 * counts[0] and counts[2] < 0.002 * counts[0]
+
+
 @pytest.mark.parametrize("n", [5, 100, 2048, 2049, 40000, 700000])
 def test_ecdf_build_and_transform(gpu, n):
     rng = np.random.default_rng(n)
