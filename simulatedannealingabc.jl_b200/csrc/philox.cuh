@@ -149,6 +149,18 @@ SABC_HD int ptrs_filter(double lam, double kf, double num, double den) {
     double T, E; return ptrs_filter(lam, kf, num, den, T, E);
 }
 
+// The PTRS constants whose low mantissa word is not zero cost two UMOV each as immediates, every loop trip; from the
+// constant bank they are one LDCU.64 (or half an LDCU.128).  Same literals on the host.
+#if defined(__CUDACC__)
+__constant__ double c_ptrs[14] = {0.931, 2.53, -0.059, 0.02483, 0.43, 0.9277, 3.6224, 0.07, 0.013, 3.4, 1.1239, 1.1328,
+                                  0x1.d67f1c864beb5p-1, 0.0};
+#endif
+#if defined(__CUDA_ARCH__) && !defined(SABC_NO_CONST_BANK)
+#define SABC_PC(i, v) c_ptrs[i]
+#else
+#define SABC_PC(i, v) (v)
+#endif
+
 #if defined(__CUDACC__)
 // log2 on the special-function unit: ONE MUFU.LG2 (arguments here are normal floats, so the flush-to-zero form needs no
 // pre-scaling).  Documented accuracy of lg2.approx: absolute error <= 2^-21.41 on [0.5, 2], <= 2 ulp elsewhere.
@@ -178,7 +190,7 @@ SABC_D int ptrs_filter_mufu(double lam, double kf, double num, double den, float
     // ln2 * [ k log2 q + log2(x)/2 + log2 num - log2 den ]
     float L = __fmaf_rn(kff, mufu_lg2(q), __fmul_rn(0.5f, mufu_lg2(xf)));
     L = __fadd_rn(L, __fsub_rn(mufu_lg2(__double2float_rn(num)), mufu_lg2(__double2float_rn(den))));
-    const float Df = __double2float_rn(D - 0x1.d67f1c864beb5p-1);
+    const float Df = __double2float_rn(D - c_ptrs[12]);
     T = __fsub_rn(__fsub_rn(Df, corr), __fmul_rn(0.693147180559945f, L));
     E = __fmaf_rn(kff, q <= 2.0f ? 1e-6f : 3e-6f, __fmaf_rn(fabsf(Df), 5e-7f, 2e-4f));
     return T > E ? 1 : (T < -E ? -1 : 0);
@@ -189,16 +201,16 @@ SABC_D int ptrs_filter_mufu(double lam, double kf, double num, double den, float
 // ptrs_candidate: 1 = accept kf, 0 = reject, 2 = the exact test on (kf, num, den) decides.
 SABC_HD int ptrs_candidate(double lam, const U64x2 w, double& kf, double& num, double& den) {
     const double slam = sqrt(lam);
-    const double b = 0.931 + 2.53 * slam;
-    const double a = -0.059 + 0.02483 * b;
+    const double b = SABC_PC(0, 0.931) + SABC_PC(1, 2.53) * slam;
+    const double a = SABC_PC(2, -0.059) + SABC_PC(3, 0.02483) * b;
     const double U = u53(w.a) - 0.5, V = u53(w.b);
     const double us = 0.5 - fabs(U);
     const double r = drcp(us);
-    kf = floor(((2.0 * a) * r + b) * U + lam + 0.43);
-    if (us >= 0.07 && (0.9277 - V) * (b - 2.0) >= 3.6224) return 1;
-    if (kf < 0.0 || (us < 0.013 && V > us)) return 0;
-    const double bm = b - 3.4;
-    num = V * (1.1239 * bm + 1.1328);
+    kf = floor(((2.0 * a) * r + b) * U + lam + SABC_PC(4, 0.43));
+    if (us >= SABC_PC(7, 0.07) && (SABC_PC(5, 0.9277) - V) * (b - 2.0) >= SABC_PC(6, 3.6224)) return 1;
+    if (kf < 0.0 || (us < SABC_PC(8, 0.013) && V > us)) return 0;
+    const double bm = b - SABC_PC(9, 3.4);
+    num = V * (SABC_PC(10, 1.1239) * bm + SABC_PC(11, 1.1328));
     den = bm * ((a * r) * r + b);
     return 2;
 }
@@ -212,8 +224,9 @@ SABC_HD bool ptrs_exact(double lam, double kf, double num, double den) {
 // rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one Philox block (none when
 // lam <= 0) and either returns a count or rejects; this is the unit the SIR kernel interleaves across lanes so that a
 // rejection in one lane does not stall the accepted lanes of its warp.  The two filters only shortcut the exact test.
-SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
-    if (!(lam > 0.0)) { k_out = 0; return true; }
+// poisson_attempt_d returns the count as an integer-valued double (what PTRS computes anyway); poisson_attempt converts.
+SABC_HD bool poisson_attempt_d(double lam, Stream& st, double& k_out) {
+    if (!(lam > 0.0)) { k_out = 0.0; return true; }
     const U64x2 w = st.draw();
     if (lam < 10.0) {
         const double U = u53(w.a);
@@ -225,7 +238,7 @@ SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
         while (U > F && k < 63) { k++; p = (p * lam) * c_rcp_int[k]; F = F + p; }
 #endif
         while (U > F && k < 1024) { k++; p = (p * lam) * rcp_int(k); F = F + p; }         // p_k = p_{k-1} λ (1/k)
-        k_out = k;
+        k_out = (double)k;
         return true;
     }
     double kf, num = 0.0, den = 0.0;
@@ -246,8 +259,14 @@ SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
         s = (int)ptrs_exact(lam, kf, num, den);
 #endif
     }
-    if (s == 1) k_out = (int64_t)kf;
+    if (s == 1) k_out = kf;
     return s == 1;
+}
+SABC_HD bool poisson_attempt(double lam, Stream& st, int64_t& k_out) {
+    double kd;
+    if (!poisson_attempt_d(lam, st, kd)) return false;
+    k_out = (int64_t)kd;
+    return true;
 }
 SABC_HD int64_t poisson(double lam, Stream& st) {
     int64_t k;

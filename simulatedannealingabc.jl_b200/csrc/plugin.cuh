@@ -315,28 +315,31 @@ struct SirTauLeap {
         const double pop = mp.v[0], tau = mp.v[2];
         const double inv_pop = drcp(pop);
         const int T = (int)mp.v[1];
-        int64_t I = (int64_t)floor(th[2] * pop + 0.5);
-        if (I < 0) I = 0;
-        if (I > (int64_t)pop) I = (int64_t)pop;
-        int64_t Sc = (int64_t)pop - I;
-        int64_t total = 0, peak = -1, tpeak = 0, ninf = 0;
+        // compartments and counts are integers below 2^53 held in FP64: exact, and no int64 <-> double conversions in the loop
+        const double popi = (double)(int64_t)pop;
+        double I = floor(th[2] * pop + 0.5);
+        if (I < 0.0) I = 0.0;
+        if (I > popi) I = popi;
+        double Sc = popi - I;
+        double total = 0.0, peak = -1.0, ninf = 0.0;
+        int tpeak = 0;
         int t = 1, phase = 0;
-        double lam = (((th[0] * (double)Sc) * (double)I) * inv_pop) * tau;
+        double lam = (((th[0] * Sc) * I) * inv_pop) * tau;
         // one accepted draw k moves the particle to its next draw
-        auto advance = [&](int64_t k) {
+        auto advance = [&](double k) {
             if (phase == 0) {
                 ninf = k > Sc ? Sc : k;
-                lam = (th[1] * (double)I) * tau;
+                lam = (th[1] * I) * tau;
                 phase = 1;
             } else if (phase == 1) {
-                const int64_t nrec = k > I ? I : k;
+                const double nrec = k > I ? I : k;
                 Sc -= ninf; I += ninf - nrec;
-                lam = th[3] * (double)ninf;
+                lam = th[3] * ninf;
                 phase = 2;
             } else {
                 total += k;
                 if (k > peak) { peak = k; tpeak = t; }
-                lam = (((th[0] * (double)Sc) * (double)I) * inv_pop) * tau;
+                lam = (((th[0] * Sc) * I) * inv_pop) * tau;
                 phase = 0; t++;
             }
         };
@@ -344,11 +347,11 @@ struct SirTauLeap {
         // one trip instead of stalling its warp.  (Parking the lanes that need the exact PTRS test or the inversion loop
         // until enough of them wait was measured and is slower: the cheap part of a trip is not cheap enough, r1 notes.)
         while (t <= T) {
-            int64_t k;
-            if (!poisson_attempt(lam, st, k)) continue;
+            double k;
+            if (!poisson_attempt_d(lam, st, k)) continue;
             advance(k);
         }
-        const double d0 = (double)total - mp.v[3], d1 = (double)peak - mp.v[4], d2 = (double)tpeak - mp.v[5];
+        const double d0 = total - mp.v[3], d1 = peak - mp.v[4], d2 = (double)tpeak - mp.v[5];
         rho[0] = d0 * d0; rho[1] = d1 * d1; rho[2] = d2 * d2;
     }
 };
