@@ -72,9 +72,22 @@ SABC_HD double det_log(double x) {
     return dk * ln2_hi - ((hfsq - corr) - f);
 }
 
+// det_exp's constants with a non-zero low mantissa word: from the constant bank on the device (one LDCU.64 / half an
+// LDCU.128 each instead of two UMOV per use); the same literals on the host
+#if defined(__CUDACC__)
+__constant__ double c_exp[8] = {0x1.62e42fee00000p-1, 0x1.a39ef35793c76p-33, 0x1.71547652b82fep+0, 4.13813679705723846039e-08,
+                                -1.65339022054652515390e-06, 6.61375632143793436117e-05, -2.77777777770155933842e-03,
+                                1.66666666666666019037e-01};
+#endif
+#if defined(__CUDA_ARCH__) && !defined(SABC_NO_CONST_BANK)
+#define SABC_EC(i, v) c_exp[i]
+#else
+#define SABC_EC(i, v) (v)
+#endif
+
 // exponential, <= 1 ulp: x = k ln2 + r, exp(r) = 1 + r + r c/(2-c)
 SABC_HD double det_exp(double x) {
-    const double ln2_hi = 0x1.62e42fee00000p-1, ln2_lo = 0x1.a39ef35793c76p-33, inv_ln2 = 0x1.71547652b82fep+0;
+    const double ln2_hi = SABC_EC(0, 0x1.62e42fee00000p-1), ln2_lo = SABC_EC(1, 0x1.a39ef35793c76p-33), inv_ln2 = SABC_EC(2, 0x1.71547652b82fep+0);
     if (x != x) return x;
     if (x > 709.782712893383973096) return dinf();
     if (x < -745.13321910194110842) return 0.0;
@@ -84,8 +97,9 @@ SABC_HD double det_exp(double x) {
     const double lo = kf * ln2_lo;
     const double r = hi - lo;
     const double t = r * r;
-    const double poly = dfma(t, dfma(t, dfma(t, dfma(t, 4.13813679705723846039e-08, -1.65339022054652515390e-06),
-                                            6.61375632143793436117e-05), -2.77777777770155933842e-03), 1.66666666666666019037e-01);
+    const double poly = dfma(t, dfma(t, dfma(t, dfma(t, SABC_EC(3, 4.13813679705723846039e-08), SABC_EC(4, -1.65339022054652515390e-06)),
+                                            SABC_EC(5, 6.61375632143793436117e-05)), SABC_EC(6, -2.77777777770155933842e-03)),
+                             SABC_EC(7, 1.66666666666666019037e-01));
     const double c = r - t * poly;
     const double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
     if (k >= -1021 && k <= 1023) return bits_f64(f64_bits(y) + ((uint64_t)(int64_t)k << 52));

@@ -241,7 +241,7 @@ static UpdateArgs make_update_args(sabc_engine* e, int half, int sub = 0, int ns
     a.pop = e->pop;
     halves(e, half, a.act_off, a.act_n, a.ina_off, a.ina_n);
     a.particle_base = (uint32_t)e->offset;
-    a.half = half; a.seed = e->seed; a.ds = e->b_ds.p; a.ecdf = e->b_ecdf.p;
+    a.half = half; a.seed = e->seed; a.rk = make_round_keys(e->seed); a.ds = e->b_ds.p; a.ecdf = e->b_ecdf.p;
     a.rho_part = e->b_rho_part.p + (int64_t)half * e->S * e->part_ld;
     a.part_ld = e->part_ld; a.n_eps = e->n_eps; a.top_doubles = e->top_doubles;
     a.prop0 = e->prop_par[0]; a.prop1 = e->prop_par[1];

@@ -166,6 +166,7 @@ struct UpdateArgs {
     uint32_t particle_base;                   // global index of local particle 0 (Philox counter)
     int32_t half;
     uint64_t seed;
+    RoundKeys rk;                             // Philox round keys of `seed` (simulation kernel's hot loop)
     int32_t slot;                             // work-list counter slot = half * MAX_SUB + sub-range
     DevState* ds;
     const EcdfStat* ecdf;                     // [S] descriptors in HBM
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, cons
 }
 
 template <class M>
-__global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kernel(const UpdateArgs a, const SplitScratch w) {
+__global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kernel(const __grid_constant__ UpdateArgs a, const SplitScratch w) {
     constexpr int D = M::D, S = M::S;
     extern __shared__ __align__(128) double s_top[];
     stage_ecdf_top(a.ecdf, S, s_top);
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
             double thp[D], rp[S], up[S];
 #pragma unroll
             for (int c = 0; c < D; ++c) thp[c] = w.theta[c * w.cap + q];
-            Stream st(a.seed, pid, sweep, KIND_MODEL);
+            Stream st(a.seed, pid, sweep, KIND_MODEL, a.rk.k);
             st.warp_mask = live;
             M::sim(thp, a.mp, st, rp);                                  // :315
             double Ssum = 0.0;

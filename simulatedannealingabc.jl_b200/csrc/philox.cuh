@@ -44,14 +44,39 @@ SABC_HD U64x2 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
     return o;
 }
 
+// The ten round keys of a seed, precomputed on the host and handed to a kernel in its parameter block: inside a hot
+// loop they are then five LDCU.128 per Philox call instead of eighteen key-schedule additions.
+struct RoundKeys { uint32_t k[20]; };
+inline RoundKeys make_round_keys(uint64_t seed) {
+    RoundKeys rk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return rk;
+}
+SABC_HD U64x2 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* rk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ rk[2 * r]; c1 = l1; c2 = h0 ^ c3 ^ rk[2 * r + 1]; c3 = l0;
+    }
+    U64x2 o;
+    o.a = (uint64_t)c0 | ((uint64_t)c1 << 32);
+    o.b = (uint64_t)c2 | ((uint64_t)c3 << 32);
+    return o;
+}
+
 // A stream = (seed, particle, sweep, kind); block j of it is one Philox call.
 struct Stream {
     uint32_t k0, k1, particle, sweep_lo, tag, next;
     uint32_t warp_mask;   // lanes known to call the model together (0: the model asks __activemask())
-    SABC_HD Stream(uint64_t seed, uint32_t particle_, uint64_t sweep, uint32_t kind)
+    const uint32_t* rk;   // optional precomputed round keys of the same seed (RoundKeys::k), else nullptr
+    SABC_HD Stream(uint64_t seed, uint32_t particle_, uint64_t sweep, uint32_t kind, const uint32_t* rk_ = nullptr)
         : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), particle(particle_), sweep_lo((uint32_t)sweep),
-          tag(kind | ((uint32_t)(sweep >> 32) << 4)), next(0), warp_mask(0) {}
-    SABC_HD U64x2 block(uint32_t j) const { return philox4x32_10(particle, sweep_lo, j, tag, k0, k1); }
+          tag(kind | ((uint32_t)(sweep >> 32) << 4)), next(0), warp_mask(0), rk(rk_) {}
+    SABC_HD U64x2 block(uint32_t j) const {
+        return rk ? philox4x32_10_rk(particle, sweep_lo, j, tag, rk) : philox4x32_10(particle, sweep_lo, j, tag, k0, k1);
+    }
     SABC_HD U64x2 draw() { return block(next++); }
 };
 
