@@ -460,13 +460,33 @@ void orc_resample_indices(const uint64_t* q, int64_t n, uint64_t seed, uint64_t 
 /* Distributions ^0.25 formulas)                                            */
 /* ------------------------------------------------------------------------------------------ */
 static const double LOG2PI = 0x1.d67f1c864beb5p+0;
-typedef struct { int32_t kind; double p0, p1, c; } prior1_t;   /* c = log σ  |  -log(b-a) */
+typedef struct { int32_t kind; double p0, p1, c; } prior1_t;   /* c = log σ  |  -log(b-a) | Gamma / Beta: log normaliser */
+
+/* log Gamma(x), x > 0 (spec §3.2): recurrence up to x >= 16, then Stirling's series through 1/(1188 x^9) */
+double orc_lgamma(double x) {
+    if (!(x > 0.0)) return INFINITY;
+    double prod = 1.0;
+    while (x < 16.0) { prod = prod * x; x = x + 1.0; }
+    double lx = orc_log(x);
+    double r = 1.0 / x, r2 = r * r;
+    double p = fma(-r2, 1.0 / 1188.0, 1.0 / 1680.0);
+    p = fma(-r2, p, 1.0 / 1260.0);
+    p = fma(-r2, p, 1.0 / 360.0);
+    p = fma(-r2, p, 1.0 / 12.0);
+    double t = (x - 0.5) * lx;
+    t = t - x;
+    t = t + 0x1.d67f1c864beb5p-1;
+    t = t + r * p;
+    return t - orc_log(prod);
+}
 
 static void prior_prepare(int32_t d, const int32_t* kind, const double* par, prior1_t* out) {
     for (int32_t c = 0; c < d; ++c) {
         out[c].kind = kind[c]; out[c].p0 = par[2 * c]; out[c].p1 = par[2 * c + 1];
         if (kind[c] == ORC_PRIOR_UNIFORM) out[c].c = -orc_log(par[2 * c + 1] - par[2 * c]);
         else if (kind[c] == ORC_PRIOR_EXPONENTIAL) out[c].c = orc_log(par[2 * c]);
+        else if (kind[c] == ORC_PRIOR_GAMMA) out[c].c = orc_lgamma(par[2 * c]) + par[2 * c] * orc_log(par[2 * c + 1]);
+        else if (kind[c] == ORC_PRIOR_BETA) out[c].c = (orc_lgamma(par[2 * c]) + orc_lgamma(par[2 * c + 1])) - orc_lgamma(par[2 * c] + par[2 * c + 1]);
         else out[c].c = orc_log(par[2 * c + 1]);
     }
 }
@@ -478,6 +498,17 @@ static double prior_logpdf(int32_t d, const prior1_t* pr, const double* th) {
         case ORC_PRIOR_NORMAL: { double z = (x - pr[c].p0) / pr[c].p1; t = -((z * z + LOG2PI) * 0.5) - pr[c].c; break; }
         case ORC_PRIOR_UNIFORM: t = (x >= pr[c].p0 && x <= pr[c].p1) ? pr[c].c : -INFINITY; break;
         case ORC_PRIOR_EXPONENTIAL: t = x >= 0.0 ? (-(x / pr[c].p0)) - pr[c].c : -INFINITY; break;
+        case ORC_PRIOR_GAMMA: {                  /* Distributions: xlogy(α-1, x) - x/θ - (lgamma(α) + α log θ) */
+            if (!(x >= 0.0)) { t = -INFINITY; break; }
+            double a1 = pr[c].p0 - 1.0;
+            double tt = a1 == 0.0 ? 0.0 : a1 * orc_log(x);
+            t = (tt - x / pr[c].p1) - pr[c].c; break; }
+        case ORC_PRIOR_BETA: {                   /* xlogy(α-1, x) + xlog1py(β-1, -x) - logbeta(α, β) on [0, 1] */
+            if (!(x >= 0.0 && x <= 1.0)) { t = -INFINITY; break; }
+            double a1 = pr[c].p0 - 1.0, b1 = pr[c].p1 - 1.0;
+            double t0 = a1 == 0.0 ? 0.0 : a1 * orc_log(x);
+            double t1 = b1 == 0.0 ? 0.0 : b1 * orc_log(1.0 - x);
+            t = (t0 + t1) - pr[c].c; break; }
         default:                                                          /* LogNormal */
             if (!(x > 0.0)) { t = -INFINITY; break; }
             { double lx = orc_log(x), z = (lx - pr[c].p0) / pr[c].p1; t = (-((z * z + LOG2PI) * 0.5) - pr[c].c) - lx; }
@@ -491,6 +522,30 @@ double orc_prior_logpdf(int32_t d, const int32_t* kind, const double* par, const
     prior_prepare(d, kind, par, pr);
     return prior_logpdf(d, pr, theta);
 }
+/* Gamma(a, 1), Marsaglia & Tsang 2000 (spec §3.3): attempt t of component comp reads blocks comp + 256 (base + 2t + 1)
+ * (normal) and comp + 256 (base + 2t + 2) (word a: acceptance uniform, word b: U^(1/a) scaling when a < 1) */
+static double gamma_std(double a, stream_t* st, uint32_t comp, uint32_t base) {
+    double ae = a < 1.0 ? a + 1.0 : a;
+    double d = ae - 1.0 / 3.0;
+    double cc = 1.0 / sqrt(9.0 * d);
+    for (uint32_t t = 0; t < 100000u; ++t) {
+        uint64_t a0, b0, a1, b1;
+        double z, z1;
+        stream_block(st, comp + 256u * (base + 2u * t + 1u), &a0, &b0);
+        orc_normal_pair(a0, b0, &z, &z1);
+        stream_block(st, comp + 256u * (base + 2u * t + 2u), &a1, &b1);
+        double v = 1.0 + cc * z;
+        if (!(v > 0.0)) continue;
+        v = (v * v) * v;
+        double rhs = ((0.5 * z) * z + d) - d * v + d * orc_log(v);
+        if (orc_log(u53_open0(a1)) < rhs) {
+            double g = d * v;
+            if (a < 1.0) g = g * orc_exp(orc_log(u53_open0(b1)) / a);
+            return g;
+        }
+    }
+    return d;
+}
 static void prior_rand(int32_t d, const prior1_t* pr, uint64_t seed, uint32_t particle, double* th) {
     stream_t st = { seed, particle, 0, KIND_PRIOR, 0 };
     for (int32_t c = 0; c < d; ++c) {
@@ -501,9 +556,18 @@ static void prior_rand(int32_t d, const prior1_t* pr, uint64_t seed, uint32_t pa
         case ORC_PRIOR_NORMAL: orc_normal_pair(a, b, &z0, &z1); th[c] = pr[c].p0 + pr[c].p1 * z0; break;
         case ORC_PRIOR_UNIFORM: th[c] = pr[c].p0 + (pr[c].p1 - pr[c].p0) * u53(a); break;
         case ORC_PRIOR_EXPONENTIAL: th[c] = pr[c].p0 * (-orc_log(u53_open0(a))); break;
+        case ORC_PRIOR_GAMMA: th[c] = pr[c].p1 * gamma_std(pr[c].p0, &st, (uint32_t)c, 0u); break;
+        case ORC_PRIOR_BETA: {
+            double g1 = gamma_std(pr[c].p0, &st, (uint32_t)c, 0u), g2 = gamma_std(pr[c].p1, &st, (uint32_t)c, 1u << 20);
+            th[c] = g1 / (g1 + g2); break; }
         default: orc_normal_pair(a, b, &z0, &z1); th[c] = orc_exp(pr[c].p0 + pr[c].p1 * z0); break;
         }
     }
+}
+void orc_prior_rand(int32_t d, const int32_t* kind, const double* par, uint64_t seed, uint32_t particle, double* theta_out) {
+    prior1_t pr[16];
+    prior_prepare(d, kind, par, pr);
+    prior_rand(d, pr, seed, particle, theta_out);
 }
 
 /* ------------------------------------------------------------------------------------------ */

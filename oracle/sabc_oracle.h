@@ -27,7 +27,7 @@ extern "C" {
 
 enum { ORC_ALG_SINGLE_EPS = 0, ORC_ALG_MULTI_EPS = 1 };
 enum { ORC_PROP_DE = 0, ORC_PROP_STRETCH = 1, ORC_PROP_RW = 2 };
-enum { ORC_PRIOR_UNIFORM = 0, ORC_PRIOR_NORMAL = 1, ORC_PRIOR_EXPONENTIAL = 2, ORC_PRIOR_LOGNORMAL = 3 };
+enum { ORC_PRIOR_UNIFORM = 0, ORC_PRIOR_NORMAL = 1, ORC_PRIOR_EXPONENTIAL = 2, ORC_PRIOR_LOGNORMAL = 3, ORC_PRIOR_GAMMA = 4, ORC_PRIOR_BETA = 5 };
 enum { ORC_MODEL_GAUSS_MEAN = 0, ORC_MODEL_GAUSS_SAMPLE = 1, ORC_MODEL_LOGISTIC = 2, ORC_MODEL_SIR = 3, ORC_MODEL_SIR_GILLESPIE = 4 };
 
 typedef struct orc_config {
@@ -73,6 +73,8 @@ void   orc_resample_weights(const double* u /* n*s col-major */, int64_t n, int3
                             double delta, double* w_out, uint64_t* q_out);
 void   orc_resample_indices(const uint64_t* q, int64_t n, uint64_t seed, uint64_t resample_count, int64_t* idx_out);
 void   orc_exact_mean_u(const double* u, int64_t n, double* mean_out);
+double orc_lgamma(double x);
+void   orc_prior_rand(int32_t d, const int32_t* kind, const double* par, uint64_t seed, uint32_t particle, double* theta_out);
 double orc_prior_logpdf(int32_t d, const int32_t* kind, const double* par, const double* theta);
 int    orc_model_simulate(int32_t model_id, int32_t d, int32_t s, const double* model_par, int32_t n_model_par,
                           const double* theta, uint64_t seed, uint32_t particle, uint64_t sweep, double* rho_out);

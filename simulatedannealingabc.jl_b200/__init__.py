@@ -7,9 +7,9 @@
 from . import _lib, models  # noqa: F401
 from ._lib import SABCError, SABC_FLAG_FUSED, SABC_FLAG_GENERIC_TAIL, SABC_FLAG_MG_REPLICATED, SABC_FLAG_NO_GRAPH, SABC_FLAG_NO_PIPELINE, SABC_FLAG_SORT_WORK, SABC_FLAG_TIME_KERNELS  # noqa: F401
 from .api import Engine, SABCresult, SABCstate, sabc, update_population  # noqa: F401
-from .distributions import Exponential, LogNormal, Normal, Product, Uniform, product_distribution  # noqa: F401
+from .distributions import Beta, Exponential, Gamma, LogNormal, Normal, Product, Uniform, product_distribution  # noqa: F401
 from .models import DeviceModel  # noqa: F401
 from .proposals import DifferentialEvolution, RandomWalk, StretchMove  # noqa: F401
 
-__all__ = ["sabc", "update_population", "SABCresult", "SABCstate", "Engine", "DeviceModel", "models", "Normal", "Uniform", "Exponential", "LogNormal",
+__all__ = ["sabc", "update_population", "SABCresult", "SABCstate", "Engine", "DeviceModel", "models", "Normal", "Uniform", "Exponential", "LogNormal", "Gamma", "Beta",
            "product_distribution", "DifferentialEvolution", "StretchMove", "RandomWalk", "SABCError"]

@@ -22,7 +22,7 @@ constexpr int CHUNK = 256;          // particles per tree-sum group == threads p
 
 enum Algorithm : int32_t { ALG_SINGLE_EPS = 0, ALG_MULTI_EPS = 1 };
 enum ProposalKind : int32_t { PROP_DE = 0, PROP_STRETCH = 1, PROP_RW = 2 };
-enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1, PRIOR_EXPONENTIAL = 2, PRIOR_LOGNORMAL = 3 };
+enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1, PRIOR_EXPONENTIAL = 2, PRIOR_LOGNORMAL = 3, PRIOR_GAMMA = 4, PRIOR_BETA = 5 };
 
 // ------------------------------------------------------------------------------------------------
 // Prior: product of independent univariates (Distributions ^0.25 formulas)
@@ -30,8 +30,9 @@ enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1, PRIOR_EXPONENTIA
 struct PriorSpec {
     int32_t n;
     int32_t kind[MAX_D];
-    double p0[MAX_D], p1[MAX_D];   // Uniform(a,b) | Normal(mu,sigma) | Exponential(theta,-) | LogNormal(mu,sigma)
+    double p0[MAX_D], p1[MAX_D];   // Uniform(a,b) | Normal(mu,sigma) | Exponential(theta,-) | LogNormal(mu,sigma) | Gamma(alpha,theta) | Beta(alpha,beta)
     double c[MAX_D];               // -log(b-a)    | log(sigma)       | log(theta)           | log(sigma)   (det_log)
+                                   // Gamma: lgamma(alpha) + alpha log(theta) | Beta: lgamma(alpha) + lgamma(beta) - lgamma(alpha+beta)
 };
 
 inline void prior_prepare(PriorSpec& p) {
@@ -39,6 +40,8 @@ inline void prior_prepare(PriorSpec& p) {
         switch (p.kind[i]) {
             case PRIOR_UNIFORM: p.c[i] = -det_log(p.p1[i] - p.p0[i]); break;
             case PRIOR_EXPONENTIAL: p.c[i] = det_log(p.p0[i]); break;
+            case PRIOR_GAMMA: p.c[i] = det_lgamma(p.p0[i]) + p.p0[i] * det_log(p.p1[i]); break;
+            case PRIOR_BETA: p.c[i] = (det_lgamma(p.p0[i]) + det_lgamma(p.p1[i])) - det_lgamma(p.p0[i] + p.p1[i]); break;
             default: p.c[i] = det_log(p.p1[i]); break;
         }
     }
@@ -53,6 +56,19 @@ SABC_HD double prior_logpdf1(int kind, double p0, double p1, double c, double x)
     }
     if (kind == PRIOR_UNIFORM) return (x >= p0 && x <= p1) ? c : -dinf();
     if (kind == PRIOR_EXPONENTIAL) return x >= 0.0 ? (-(x / p0)) - c : -dinf();
+    if (kind == PRIOR_GAMMA) {                               // (alpha-1) log x - x/theta - c, xlogy(0, 0) = 0 at the edge
+        if (!(x >= 0.0)) return -dinf();
+        const double a1 = p0 - 1.0;
+        const double t = a1 == 0.0 ? 0.0 : a1 * det_log(x);
+        return (t - x / p1) - c;
+    }
+    if (kind == PRIOR_BETA) {                                // (alpha-1) log x + (beta-1) log(1-x) - c on [0, 1]
+        if (!(x >= 0.0 && x <= 1.0)) return -dinf();
+        const double a1 = p0 - 1.0, b1 = p1 - 1.0;
+        const double t0 = a1 == 0.0 ? 0.0 : a1 * det_log(x);
+        const double t1 = b1 == 0.0 ? 0.0 : b1 * det_log(1.0 - x);
+        return (t0 + t1) - c;
+    }
     if (!(x > 0.0)) return -dinf();                         // LogNormal
     const double lx = det_log(x);
     const double z = (lx - p0) / p1;
@@ -70,6 +86,31 @@ SABC_HD double prior_logpdf(const PriorSpec& p, const double (&th)[D]) {
     return lp;
 }
 
+// Gamma(a, 1) by Marsaglia & Tsang (2000): d = a - 1/3 (a + 1 - 1/3 below 1, then the draw is scaled by U^(1/a)),
+// v = (1 + z / sqrt(9 d))^3, accept when log(U) < z^2/2 + d - d v + d log v.  Attempt t of component `comp` reads the
+// prior stream's blocks comp + 256 (base + 2t + 1) [normal pair, first output] and comp + 256 (base + 2t + 2)
+// [word a: acceptance uniform, word b: the scaling uniform for a < 1]; block `comp` itself stays with the one-block families.
+SABC_HD double gamma_std(double a, const Stream& st, uint32_t comp, uint32_t base) {
+    const double ae = a < 1.0 ? a + 1.0 : a;
+    const double d = ae - 1.0 / 3.0;
+    const double cc = 1.0 / sqrt(9.0 * d);
+    for (uint32_t t = 0; t < 100000u; ++t) {
+        double z, z1;
+        normal_pair(st.block(comp + 256u * (base + 2u * t + 1u)), z, z1);
+        const U64x2 w = st.block(comp + 256u * (base + 2u * t + 2u));
+        double v = 1.0 + cc * z;
+        if (!(v > 0.0)) continue;
+        v = (v * v) * v;
+        const double rhs = ((0.5 * z) * z + d) - d * v + d * det_log(v);
+        if (det_log(u53_open0(w.a)) < rhs) {
+            double g = d * v;
+            if (a < 1.0) g = g * det_exp(det_log(u53_open0(w.b)) / a);
+            return g;
+        }
+    }
+    return d;
+}
+
 template <int D>
 SABC_HD void prior_rand(const PriorSpec& p, uint64_t seed, uint32_t particle, double (&th)[D]) {
     const Stream st(seed, particle, 0, KIND_PRIOR);
@@ -81,6 +122,12 @@ SABC_HD void prior_rand(const PriorSpec& p, uint64_t seed, uint32_t particle, do
             case PRIOR_NORMAL: normal_pair(w, z0, z1); th[c] = p.p0[c] + p.p1[c] * z0; break;
             case PRIOR_UNIFORM: th[c] = p.p0[c] + (p.p1[c] - p.p0[c]) * u53(w.a); break;
             case PRIOR_EXPONENTIAL: th[c] = p.p0[c] * (-det_log(u53_open0(w.a))); break;
+            case PRIOR_GAMMA: th[c] = p.p1[c] * gamma_std(p.p0[c], st, (uint32_t)c, 0u); break;
+            case PRIOR_BETA: {
+                const double g1 = gamma_std(p.p0[c], st, (uint32_t)c, 0u), g2 = gamma_std(p.p1[c], st, (uint32_t)c, 1u << 20);
+                th[c] = g1 / (g1 + g2);
+                break;
+            }
             default: normal_pair(w, z0, z1); th[c] = det_exp(p.p0[c] + p.p1[c] * z0); break;
         }
     }

@@ -1,11 +1,12 @@
 """Priors: the subset of Distributions.jl the reference's tests and docs use (Uniform, Normal and
-product_distribution of them; test/runtests.jl:36,87-88,125,163-164, docs/src/usage.md:20-21).  The objects only
-carry parameters; sampling and log-density run on the device (csrc/plugin.cuh)."""
+product_distribution of them; test/runtests.jl:36,87-88,125,163-164, docs/src/usage.md:20-21) plus Exponential,
+LogNormal, Gamma and Beta with Distributions.jl's parametrisations.  The objects only carry parameters; sampling and
+log-density run on the device (csrc/plugin.cuh)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
 
-PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_EXPONENTIAL, PRIOR_LOGNORMAL = 0, 1, 2, 3
+PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_EXPONENTIAL, PRIOR_LOGNORMAL, PRIOR_GAMMA, PRIOR_BETA = 0, 1, 2, 3, 4, 5
 
 
 class Distribution:
@@ -75,14 +76,44 @@ class LogNormal(Distribution):
         return (float(self.mu), float(self.sigma))
 
 
-UNIVARIATE = (Uniform, Normal, Exponential, LogNormal)
+@dataclass(frozen=True)
+class Gamma(Distribution):
+    alpha: float = 1.0            # shape
+    theta: float = 1.0            # scale, as in Distributions.Gamma(α, θ)
+
+    def __post_init__(self):
+        if not (self.alpha > 0 and self.theta > 0):
+            raise ValueError("Gamma: the condition α > zero(α) && θ > zero(θ) is not satisfied")
+
+    kind = PRIOR_GAMMA
+
+    def params(self):
+        return (float(self.alpha), float(self.theta))
+
+
+@dataclass(frozen=True)
+class Beta(Distribution):
+    alpha: float = 1.0
+    beta: float = 1.0
+
+    def __post_init__(self):
+        if not (self.alpha > 0 and self.beta > 0):
+            raise ValueError("Beta: the condition α > zero(α) && β > zero(β) is not satisfied")
+
+    kind = PRIOR_BETA
+
+    def params(self):
+        return (float(self.alpha), float(self.beta))
+
+
+UNIVARIATE = (Uniform, Normal, Exponential, LogNormal, Gamma, Beta)
 
 
 class Product(Distribution):
     def __init__(self, dists):
         self.dists = list(dists)
         if not self.dists or not all(isinstance(d, UNIVARIATE) for d in self.dists):
-            raise TypeError("product_distribution supports Uniform, Normal, Exponential and LogNormal components on the device path")
+            raise TypeError("product_distribution supports Uniform, Normal, Exponential, LogNormal, Gamma and Beta components on the device path")
 
     def components(self):
         return self.dists

@@ -26,6 +26,7 @@ CASES = [  # name, N, updates, algorithm, proposal
     ("logistic", 1200, 15, "single_eps", "de"),
     ("sir_tauleap", 1024, 12, "single_eps", "de"),
     ("sir_gillespie_s3", 2000, 20, "multi_eps", "de"),
+    ("gauss_sample_d2s2_gambeta", 1000, 20, "multi_eps", "de"),   # Gamma x Beta prior
 ]
 
 

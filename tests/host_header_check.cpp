@@ -1,6 +1,7 @@
 // host_header_check.cpp -- TEST CODE (links the oracle).  The product's sampler and model headers are written for host and
 // device (SABC_HD); compiled here with g++ they must reproduce the oracle bit for bit: Poisson draws (inversion, PTRS with
-// the FP64 acceptance filter in front of the exact test) and whole SIR tau-leap simulations.  This pins the header logic
+// the FP64 acceptance filter in front of the exact test), whole SIR tau-leap simulations, prior draws and log-densities of
+// every family.  This pins the header logic
 // on the CPU; the GPU parity tests pin the device build of the same headers (which adds the MUFU filter and the tables).
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +11,8 @@ extern "C" {
 int orc_model_simulate(int32_t model_id, int32_t d, int32_t s, const double* model_par, int32_t n_model_par, const double* theta,
                        uint64_t seed, uint32_t particle, uint64_t sweep, double* rho_out);
 int64_t orc_poisson(double lam, uint64_t seed, uint32_t particle, uint64_t sweep, uint32_t* block_io);
+void orc_prior_rand(int32_t d, const int32_t* kind, const double* par, uint64_t seed, uint32_t particle, double* theta_out);
+double orc_prior_logpdf(int32_t d, const int32_t* kind, const double* par, const double* theta);
 }
 using namespace sabc;
 
@@ -47,6 +50,31 @@ int main(int argc, char** argv) {
         orc_model_simulate(3, 4, 3, par, 6, th, 77, (uint32_t)i, 5, ro);
         if (memcmp(rho, ro, sizeof rho) != 0) { if (bad < 10) printf("sir mismatch %d\n", i); bad++; }
     }
-    printf("%d poisson draws, %d sir simulations, %ld mismatches\n", n_draw, n_sim, bad);
+    // priors: every family, draws and log-densities (also off the support)
+    const int n_prior = 20000;
+    const int32_t kinds[3][6] = {{4, 5, 0, 1, 2, 3}, {5, 4, 4, 5, 4, 5}, {4, 4, 5, 5, 1, 0}};
+    const double pars[3][12] = {{2.5, 0.8, 0.7, 3.0, -1.0, 3.0, 0.5, 2.0, 1.5, 0.0, 0.5, 0.8},
+                                {4.0, 2.0, 0.4, 1.5, 1.0, 3.0, 1.0, 1.0, 30.0, 0.01, 0.05, 0.05},
+                                {0.05, 1.0, 100.0, 2.0, 0.5, 0.5, 50.0, 60.0, 0.0, 1.0, 0.0, 1.0}};
+    for (int set = 0; set < 3; ++set) {
+        PriorSpec ps{};
+        ps.n = 6;
+        for (int c = 0; c < 6; ++c) { ps.kind[c] = kinds[set][c]; ps.p0[c] = pars[set][2 * c]; ps.p1[c] = pars[set][2 * c + 1]; }
+        prior_prepare(ps);
+        for (int i = 0; i < n_prior; ++i) {
+            double th[6], to[6];
+            prior_rand<6>(ps, 4242, (uint32_t)i, th);
+            orc_prior_rand(6, kinds[set], pars[set], 4242, (uint32_t)i, to);
+            if (memcmp(th, to, sizeof th) != 0) { if (bad < 10) printf("prior_rand mismatch set %d particle %d\n", set, i); bad++; continue; }
+            if (i % 5 == 1) th[i % 6] = -th[i % 6];
+            if (i % 5 == 2) th[i % 6] = th[i % 6] + 1.0;
+            if (i % 97 == 0) th[i % 6] = 0.0;
+            if (i % 89 == 0) th[i % 6] = 1.0;
+            const double(&thr)[6] = th;
+            const double lp = prior_logpdf<6>(ps, thr), lo = orc_prior_logpdf(6, kinds[set], pars[set], th);
+            if (memcmp(&lp, &lo, 8) != 0 && !(lp != lp && lo != lo)) { if (bad < 10) printf("prior_logpdf mismatch set %d particle %d: %.17g vs %.17g\n", set, i, lp, lo); bad++; }
+        }
+    }
+    printf("%d poisson draws, %d sir simulations, %d x 3 prior draws, %ld mismatches\n", n_draw, n_sim, n_prior, bad);
     return bad != 0;
 }

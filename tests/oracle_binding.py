@@ -60,7 +60,8 @@ def lib() -> C.CDLL:
             "orc_resample_weights": (None, [vp, i64, i32, vp, dbl, vp, vp]),
             "orc_resample_indices": (None, [vp, i64, u64, u64, vp]),
             "orc_exact_mean_u": (None, [vp, i64, C.POINTER(dbl)]),
-            "orc_prior_logpdf": (dbl, [i32, vp, vp, vp]),
+            "orc_prior_logpdf": (dbl, [i32, vp, vp, vp]), "orc_lgamma": (dbl, [dbl]),
+            "orc_prior_rand": (None, [i32, vp, vp, u64, u32, vp]),
             "orc_model_simulate": (C.c_int, [i32, i32, i32, vp, i32, vp, u64, u32, u64, vp]),
             "orc_propose": (C.c_int, [i32, vp, i32, vp, vp, i64, vp, u64, u32, u64, vp, C.POINTER(dbl)]),
             "orc_create": (C.c_int, [C.POINTER(vp), C.POINTER(OrcConfig)]), "orc_destroy": (C.c_int, [vp]),

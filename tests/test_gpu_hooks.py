@@ -208,6 +208,25 @@ def test_prior_logpdf(gpu):
     assert np.allclose(lp[ok], ref, rtol=1e-12, atol=1e-12) and np.all(np.isneginf(lp[~ok]))
 
 
+def test_prior_logpdf_gamma_beta(gpu):
+    """Gamma(alpha, theta) and Beta(alpha, beta): device == oracle bit for bit, both == scipy, Distributions.jl edge values."""
+    from scipy import stats
+    rng = np.random.default_rng(6)
+    for (a, th_), (al, be) in [((2.5, 0.8), (0.7, 3.0)), ((1.0, 2.0), (1.0, 1.0)), ((0.4, 1.5), (2.0, 0.5))]:
+        kind = np.array([4, 5], dtype=np.int32); par = np.array([a, th_, al, be])
+        th = np.asfortranarray(np.column_stack([rng.uniform(-1, 8, 4000), rng.uniform(-0.2, 1.2, 4000)]))
+        th[:4] = [[0.0, 0.5], [1.0, 0.0], [1.0, 1.0], [0.0, 0.0]]
+        lp = np.zeros(4000)
+        L.check(L.lib().sabc_prior_logpdf(2, ptr(kind), ptr(par), ptr(th), 4000, ptr(lp)))
+        want = np.array([ob.lib().orc_prior_logpdf(2, ob.p(kind), ob.p(par), ob.p(np.ascontiguousarray(th[i]))) for i in range(4000)])
+        assert np.array_equal(lp, want)
+        ok = (th[:, 0] > 0) & (th[:, 1] > 0) & (th[:, 1] < 1)
+        ref = stats.gamma(a, scale=th_).logpdf(th[ok, 0]) + stats.beta(al, be).logpdf(th[ok, 1])
+        assert np.allclose(lp[ok], ref, rtol=1e-11, atol=1e-11)
+        out = (th[:, 0] < 0) | (th[:, 1] < 0) | (th[:, 1] > 1)
+        assert np.all(np.isneginf(lp[out]))
+
+
 @pytest.mark.parametrize("name", list(model_cases().keys()))
 def test_model_simulate_bit_exact(gpu, name):
     model, prior = model_cases()[name]

@@ -154,3 +154,15 @@ def test_exchange_plan_is_consistent():
                 assert np.all(sent == 1)
     bad = np.array([3, 3], dtype=np.int64); arrs = [np.zeros(2, dtype=np.int64) for _ in range(4)]
     assert sb._lib.lib().sabc_mg_exchange_plan(sb._lib.ptr(bad), 2, 4, 0, *[sb._lib.ptr(a) for a in arrs]) == -20
+
+
+def test_prior_constructors_validate_like_distributions_jl():
+    """Distributions.jl throws DomainError for invalid parameters at construction; the mirror raises ValueError."""
+    for bad in (lambda: sb.Uniform(1.0, 1.0), lambda: sb.Normal(0.0, 0.0), lambda: sb.Exponential(-1.0), lambda: sb.LogNormal(0.0, -1.0),
+                lambda: sb.Gamma(0.0, 1.0), lambda: sb.Gamma(1.0, -2.0), lambda: sb.Beta(-1.0, 1.0), lambda: sb.Beta(1.0, 0.0)):
+        with pytest.raises(ValueError):
+            bad()
+    p = sb.product_distribution([sb.Gamma(2.0, 0.5), sb.Beta(2.0, 3.0), sb.Uniform(0, 1)])
+    assert len(p) == 3 and [c.kind for c in p.components()] == [4, 5, 0] and p.components()[0].params() == (2.0, 0.5)
+    with pytest.raises(TypeError):
+        sb.product_distribution([sb.Gamma(2.0, 0.5), "Normal(0,1)"])

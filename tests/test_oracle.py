@@ -229,3 +229,31 @@ def test_posterior_conjugate():
         th = o.get_population()[0][:, 0]; ms.append(th.mean()); vs.append(th.var())
     assert abs(np.mean(ms) - 10 / 11) < 2 * np.std(ms, ddof=1) / math.sqrt(6)
     assert abs(np.mean(vs) - 1 / 11) < 2 * np.std(vs, ddof=1) / math.sqrt(6)
+
+
+def test_gamma_beta_priors():
+    """Gamma / Beta priors of the spec: log Gamma against scipy, log-density against scipy (with Distributions.jl's edge
+    values), Marsaglia-Tsang draws against the exact distributions (KS)."""
+    from scipy import special, stats
+    L = ob.lib()
+    xs = np.concatenate([10 ** np.random.default_rng(0).uniform(-6, 4, 2000), [0.5, 1.0, 2.0, 15.999, 16.0, 100.0]])
+    got = np.array([L.orc_lgamma(float(x)) for x in xs])
+    assert np.allclose(got, special.gammaln(xs), rtol=2e-14, atol=2e-14)
+    # log-density edges: Gamma(1, theta) at 0 is -log(theta); alpha > 1 gives -Inf, alpha < 1 +Inf (xlogy semantics)
+    k = np.array([4], dtype=np.int32)
+    lp = lambda a, t, x: L.orc_prior_logpdf(1, ob.p(k), ob.p(np.array([a, t])), ob.p(np.array([x])))
+    assert abs(lp(1.0, 2.0, 0.0) + np.log(2.0)) < 1e-14 and lp(2.0, 1.0, 0.0) == -np.inf and lp(0.5, 1.0, 0.0) == np.inf
+    assert lp(2.0, 1.0, -1e-9) == -np.inf
+    kb = np.array([5], dtype=np.int32)
+    lpb = lambda a, b, x: L.orc_prior_logpdf(1, ob.p(kb), ob.p(np.array([a, b])), ob.p(np.array([x])))
+    assert abs(lpb(1.0, 1.0, 0.0)) < 1e-14 and abs(lpb(1.0, 1.0, 1.0)) < 1e-14 and lpb(2.0, 2.0, 1.5) == -np.inf
+    # draws
+    n = 20000
+    for kind, par, dist in [(4, (2.5, 0.8), stats.gamma(2.5, scale=0.8)), (4, (0.4, 1.5), stats.gamma(0.4, scale=1.5)),
+                            (4, (1.0, 3.0), stats.gamma(1.0, scale=3.0)), (5, (0.7, 3.0), stats.beta(0.7, 3.0)),
+                            (5, (4.0, 2.0), stats.beta(4.0, 2.0))]:
+        kk = np.array([kind], dtype=np.int32); pp = np.array(par)
+        out = np.zeros(1); x = np.empty(n)
+        for i in range(n):
+            L.orc_prior_rand(1, ob.p(kk), ob.p(pp), 99, i, ob.p(out)); x[i] = out[0]
+        assert stats.kstest(x, dist.cdf).pvalue > 1e-3, (kind, par)
