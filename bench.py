@@ -287,12 +287,17 @@ def main():
     achieved = bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_hbm()
     traffic = None                         # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    pipes = None                           # and its pipe utilisation from the same capture (what actually bounds a non-HBM kernel)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        key = None
         if model.name == "sir_tauleap" and n_per_gpu == 1_250_000:
-            traffic = tr.get("simulate_accept_kernel<sir_tauleap>")
+            key = "simulate_accept_kernel<sir_tauleap>"
         elif model.name == "gauss_mean" and n_per_gpu == 10_000_000:
-            traffic = tr.get("update_half_kernel<gauss_mean, DE>@5000000")
+            key = "update_half_kernel<gauss_mean, DE>@5000000"
+        if key:
+            traffic = tr.get(key)
+            pipes = tr.get("pipes", {}).get(key)
     except Exception:
         pass
 
@@ -351,7 +356,7 @@ def main():
                                 if model.name in ("sir_tauleap", "logistic") else f"update_half_kernel<{model.name}, DE>"), "avg_kernel_ms": avg_kernel_ms, "kernel_launches": int(kernel_launches),
                      "kernel_share_of_step": kernel_ms / t["update_ms"] if time_kernels_live else None,
                      "algorithmic_bytes_per_update": bytes_per_update, "updates_per_launch": n_per_gpu / 2, "peak_source": peak_src,
-                     "grid": kinfo, "timing": how,
+                     "grid": kinfo, "timing": how, "ncu_pipes": pipes,
                      "note": ("simulation-heavy model: FP64/INT-issue and divergence bound, not HBM bound (DESIGN.md section 4); profiles/ holds the pipe utilisation"
                               if model.name in ("sir_tauleap", "logistic") else "state streaming + ECDF leaf sectors (DESIGN.md section 4)")},
         "clocks": sampler.summary(),
