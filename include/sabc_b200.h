@@ -43,7 +43,9 @@ extern "C" {
 enum { SABC_ALG_SINGLE_EPS = 0, SABC_ALG_MULTI_EPS = 1 };          /* algorithm = :single_eps | :multi_eps  (:453) */
 enum { SABC_PROP_DE = 0, SABC_PROP_STRETCH = 1, SABC_PROP_RW = 2 }; /* src/proposals.jl:85,132,24 */
 enum { SABC_PRIOR_UNIFORM = 0, SABC_PRIOR_NORMAL = 1, SABC_PRIOR_EXPONENTIAL = 2, SABC_PRIOR_LOGNORMAL = 3,
-       SABC_PRIOR_GAMMA = 4 /* (shape, scale) */, SABC_PRIOR_BETA = 5 };                                          /* Distributions.jl */
+       SABC_PRIOR_GAMMA = 4 /* (shape, scale) */, SABC_PRIOR_BETA = 5, SABC_PRIOR_CAUCHY = 6 /* (mu, sigma) */,
+       SABC_PRIOR_LAPLACE = 7 /* (mu, theta) */, SABC_PRIOR_WEIBULL = 8 /* (shape, scale) */,
+       SABC_PRIOR_INVERSEGAMMA = 9 /* (shape, scale) */ };                                                         /* Distributions.jl */
 
 typedef struct sabc_engine sabc_engine;
 
@@ -65,7 +67,7 @@ typedef struct sabc_config {
     int32_t  n_model_par;
     int32_t  device;          /* CUDA device ordinal; -1 = current device */
     const int32_t* prior_kind;/* n_para entries, SABC_PRIOR_* */
-    const double*  prior_par; /* 2*n_para entries: Uniform (a,b) | Normal (mu,sigma) | Exponential (theta,0) | LogNormal (mu,sigma) | Gamma (alpha,theta) | Beta (alpha,beta) */
+    const double*  prior_par; /* 2*n_para entries: Uniform (a,b) | Normal (mu,sigma) | Exponential (theta,0) | LogNormal (mu,sigma) | Gamma (alpha,theta) | Beta (alpha,beta) | Cauchy (mu,sigma) | Laplace (mu,theta) | Weibull (alpha,theta) | InverseGamma (alpha,theta) */
     /* multi-GPU: one process per GPU, this rank owns a contiguous slice of n_particles/world_size */
     int32_t  rank, world_size;
     const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; NULL when world_size == 1 */

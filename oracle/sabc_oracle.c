@@ -180,6 +180,7 @@ static void stream_next(stream_t* st, uint64_t* a, uint64_t* b) { stream_block(s
 
 static inline double u53(uint64_t x) { return (double)(x >> 11) * 0x1p-53; }            /* [0,1)  */
 static inline double u53_open0(uint64_t x) { return (double)((x >> 11) + 1) * 0x1p-53; } /* (0,1]  */
+static inline double u53_mid(uint64_t x) { return ((double)(x >> 11) + 0.5) * 0x1p-53; }   /* (0,1)  */
 static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 
 /* Box-Muller pair from one block (53-bit uniforms) -- stands in for randn() */
@@ -487,6 +488,9 @@ static void prior_prepare(int32_t d, const int32_t* kind, const double* par, pri
         else if (kind[c] == ORC_PRIOR_EXPONENTIAL) out[c].c = orc_log(par[2 * c]);
         else if (kind[c] == ORC_PRIOR_GAMMA) out[c].c = orc_lgamma(par[2 * c]) + par[2 * c] * orc_log(par[2 * c + 1]);
         else if (kind[c] == ORC_PRIOR_BETA) out[c].c = (orc_lgamma(par[2 * c]) + orc_lgamma(par[2 * c + 1])) - orc_lgamma(par[2 * c] + par[2 * c + 1]);
+        else if (kind[c] == ORC_PRIOR_LAPLACE) out[c].c = orc_log(2.0 * par[2 * c + 1]);
+        else if (kind[c] == ORC_PRIOR_WEIBULL) out[c].c = orc_log(par[2 * c] / par[2 * c + 1]);
+        else if (kind[c] == ORC_PRIOR_INVGAMMA) out[c].c = orc_lgamma(par[2 * c]) - par[2 * c] * orc_log(par[2 * c + 1]);
         else out[c].c = orc_log(par[2 * c + 1]);
     }
 }
@@ -509,6 +513,18 @@ static double prior_logpdf(int32_t d, const prior1_t* pr, const double* th) {
             double t0 = a1 == 0.0 ? 0.0 : a1 * orc_log(x);
             double t1 = b1 == 0.0 ? 0.0 : b1 * orc_log(1.0 - x);
             t = (t0 + t1) - pr[c].c; break; }
+        case ORC_PRIOR_CAUCHY: {                 /* -(log1psq(z) + logπ + log σ) */
+            double z = (x - pr[c].p0) / pr[c].p1;
+            t = -((orc_log(1.0 + z * z) + 0x1.250d048e7a1bdp+0) + pr[c].c); break; }
+        case ORC_PRIOR_LAPLACE: t = -(fabs(x - pr[c].p0) / pr[c].p1 + pr[c].c); break;   /* -(|x-μ|/θ + log 2θ) */
+        case ORC_PRIOR_WEIBULL: {                /* log(α/θ) + xlogy(α-1, z) - z^α, z = x/θ */
+            if (!(x >= 0.0)) { t = -INFINITY; break; }
+            double lz = orc_log(x / pr[c].p1), a1 = pr[c].p0 - 1.0;
+            double tt = a1 == 0.0 ? 0.0 : a1 * lz;
+            t = (pr[c].c + tt) - orc_exp(pr[c].p0 * lz); break; }
+        case ORC_PRIOR_INVGAMMA:                 /* α log θ - lgamma(α) - (α+1) log x - θ/x */
+            if (!(x > 0.0)) { t = -INFINITY; break; }
+            t = (-((pr[c].p0 + 1.0) * orc_log(x)) - pr[c].p1 / x) - pr[c].c; break;
         default:                                                          /* LogNormal */
             if (!(x > 0.0)) { t = -INFINITY; break; }
             { double lx = orc_log(x), z = (lx - pr[c].p0) / pr[c].p1; t = (-((z * z + LOG2PI) * 0.5) - pr[c].c) - lx; }
@@ -560,6 +576,14 @@ static void prior_rand(int32_t d, const prior1_t* pr, uint64_t seed, uint32_t pa
         case ORC_PRIOR_BETA: {
             double g1 = gamma_std(pr[c].p0, &st, (uint32_t)c, 0u), g2 = gamma_std(pr[c].p1, &st, (uint32_t)c, 1u << 20);
             th[c] = g1 / (g1 + g2); break; }
+        case ORC_PRIOR_CAUCHY: {                 /* quantile μ + σ tan(π(u - 1/2)) = μ - σ cos(πu)/sin(πu), u in (0,1) */
+            double sn, cs; orc_sincos2pi(0.5 * u53_mid(a), &sn, &cs);
+            th[c] = pr[c].p0 - pr[c].p1 * (cs / sn); break; }
+        case ORC_PRIOR_LAPLACE: {                /* quantile */
+            double u = u53_mid(a);
+            th[c] = u < 0.5 ? pr[c].p0 + pr[c].p1 * orc_log(2.0 * u) : pr[c].p0 - pr[c].p1 * orc_log(2.0 * (1.0 - u)); break; }
+        case ORC_PRIOR_WEIBULL: th[c] = pr[c].p1 * orc_exp(orc_log(-orc_log(u53_open0(a))) / pr[c].p0); break;   /* θ E^(1/α) */
+        case ORC_PRIOR_INVGAMMA: th[c] = pr[c].p1 / gamma_std(pr[c].p0, &st, (uint32_t)c, 0u); break;
         default: orc_normal_pair(a, b, &z0, &z1); th[c] = orc_exp(pr[c].p0 + pr[c].p1 * z0); break;
         }
     }

@@ -27,7 +27,8 @@ extern "C" {
 
 enum { ORC_ALG_SINGLE_EPS = 0, ORC_ALG_MULTI_EPS = 1 };
 enum { ORC_PROP_DE = 0, ORC_PROP_STRETCH = 1, ORC_PROP_RW = 2 };
-enum { ORC_PRIOR_UNIFORM = 0, ORC_PRIOR_NORMAL = 1, ORC_PRIOR_EXPONENTIAL = 2, ORC_PRIOR_LOGNORMAL = 3, ORC_PRIOR_GAMMA = 4, ORC_PRIOR_BETA = 5 };
+enum { ORC_PRIOR_UNIFORM = 0, ORC_PRIOR_NORMAL = 1, ORC_PRIOR_EXPONENTIAL = 2, ORC_PRIOR_LOGNORMAL = 3, ORC_PRIOR_GAMMA = 4, ORC_PRIOR_BETA = 5,
+       ORC_PRIOR_CAUCHY = 6, ORC_PRIOR_LAPLACE = 7, ORC_PRIOR_WEIBULL = 8, ORC_PRIOR_INVGAMMA = 9 };
 enum { ORC_MODEL_GAUSS_MEAN = 0, ORC_MODEL_GAUSS_SAMPLE = 1, ORC_MODEL_LOGISTIC = 2, ORC_MODEL_SIR = 3, ORC_MODEL_SIR_GILLESPIE = 4 };
 
 typedef struct orc_config {

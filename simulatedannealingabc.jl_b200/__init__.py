@@ -7,9 +7,10 @@
 from . import _lib, models  # noqa: F401
 from ._lib import SABCError, SABC_FLAG_FUSED, SABC_FLAG_GENERIC_TAIL, SABC_FLAG_MG_REPLICATED, SABC_FLAG_NO_GRAPH, SABC_FLAG_NO_PIPELINE, SABC_FLAG_SORT_WORK, SABC_FLAG_TIME_KERNELS  # noqa: F401
 from .api import Engine, SABCresult, SABCstate, sabc, update_population  # noqa: F401
-from .distributions import Beta, Exponential, Gamma, LogNormal, Normal, Product, Uniform, product_distribution  # noqa: F401
+from .distributions import (Beta, Cauchy, Exponential, Gamma, InverseGamma, Laplace, LogNormal, Normal, Product, Uniform,  # noqa: F401
+                            Weibull, product_distribution)
 from .models import DeviceModel  # noqa: F401
 from .proposals import DifferentialEvolution, RandomWalk, StretchMove  # noqa: F401
 
-__all__ = ["sabc", "update_population", "SABCresult", "SABCstate", "Engine", "DeviceModel", "models", "Normal", "Uniform", "Exponential", "LogNormal", "Gamma", "Beta",
+__all__ = ["sabc", "update_population", "SABCresult", "SABCstate", "Engine", "DeviceModel", "models", "Normal", "Uniform", "Exponential", "LogNormal", "Gamma", "Beta", "Cauchy", "Laplace", "Weibull", "InverseGamma",
            "product_distribution", "DifferentialEvolution", "StretchMove", "RandomWalk", "SABCError"]

@@ -575,12 +575,12 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     e->prior.n = e->D;
     for (int k = 0; k < e->D; ++k) {
         e->prior.kind[k] = c->prior_kind[k]; e->prior.p0[k] = c->prior_par[2 * k]; e->prior.p1[k] = c->prior_par[2 * k + 1];
-        if (c->prior_kind[k] < SABC_PRIOR_UNIFORM || c->prior_kind[k] > SABC_PRIOR_BETA) {
+        if (c->prior_kind[k] < SABC_PRIOR_UNIFORM || c->prior_kind[k] >= PRIOR_KIND_END) {
             delete e; return set_error(SABC_ERR_INVALID, "unknown prior kind %d", c->prior_kind[k]);
         }
-        if ((c->prior_kind[k] == SABC_PRIOR_GAMMA || c->prior_kind[k] == SABC_PRIOR_BETA) &&
-            !(c->prior_par[2 * k] > 0.0 && c->prior_par[2 * k + 1] > 0.0)) {
-            delete e; return set_error(SABC_ERR_INVALID, "Gamma / Beta prior: both parameters must be positive");
+        if (!prior_params_valid(c->prior_kind[k], c->prior_par[2 * k], c->prior_par[2 * k + 1])) {
+            delete e; return set_error(SABC_ERR_INVALID, "prior component %d (kind %d): parameters (%g, %g) are outside the distribution's domain",
+                                       k, c->prior_kind[k], c->prior_par[2 * k], c->prior_par[2 * k + 1]);
         }
     }
     prior_prepare(e->prior);

@@ -82,6 +82,7 @@ struct Stream {
 
 SABC_HD double u53(uint64_t x) { return (double)(x >> 11) * 0x1p-53; }              // [0,1)
 SABC_HD double u53_open0(uint64_t x) { return (double)((x >> 11) + 1) * 0x1p-53; }  // (0,1]
+SABC_HD double u53_mid(uint64_t x) { return ((double)(x >> 11) + 0.5) * 0x1p-53; }   // (0,1), for quantile transforms
 
 // Box-Muller pair from one block; stands in for randn()
 SABC_HD void normal_pair(const U64x2 w, double& z0, double& z1) {

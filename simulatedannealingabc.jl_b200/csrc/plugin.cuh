@@ -22,7 +22,8 @@ constexpr int CHUNK = 256;          // particles per tree-sum group == threads p
 
 enum Algorithm : int32_t { ALG_SINGLE_EPS = 0, ALG_MULTI_EPS = 1 };
 enum ProposalKind : int32_t { PROP_DE = 0, PROP_STRETCH = 1, PROP_RW = 2 };
-enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1, PRIOR_EXPONENTIAL = 2, PRIOR_LOGNORMAL = 3, PRIOR_GAMMA = 4, PRIOR_BETA = 5 };
+enum PriorKind : int32_t { PRIOR_UNIFORM = 0, PRIOR_NORMAL = 1, PRIOR_EXPONENTIAL = 2, PRIOR_LOGNORMAL = 3, PRIOR_GAMMA = 4, PRIOR_BETA = 5,
+                           PRIOR_CAUCHY = 6, PRIOR_LAPLACE = 7, PRIOR_WEIBULL = 8, PRIOR_INVGAMMA = 9, PRIOR_KIND_END = 10 };
 
 // ------------------------------------------------------------------------------------------------
 // Prior: product of independent univariates (Distributions ^0.25 formulas)
@@ -33,7 +34,20 @@ struct PriorSpec {
     double p0[MAX_D], p1[MAX_D];   // Uniform(a,b) | Normal(mu,sigma) | Exponential(theta,-) | LogNormal(mu,sigma) | Gamma(alpha,theta) | Beta(alpha,beta)
     double c[MAX_D];               // -log(b-a)    | log(sigma)       | log(theta)           | log(sigma)   (det_log)
                                    // Gamma: lgamma(alpha) + alpha log(theta) | Beta: lgamma(alpha) + lgamma(beta) - lgamma(alpha+beta)
+                                   // Cauchy(mu,sigma): log(sigma) | Laplace(mu,theta): log(2 theta) | Weibull(alpha,theta): log(alpha/theta)
+                                   // InverseGamma(alpha,theta): lgamma(alpha) - alpha log(theta)
 };
+
+// parameter domains of Distributions.jl's constructors
+inline bool prior_params_valid(int kind, double p0, double p1) {
+    switch (kind) {
+        case PRIOR_UNIFORM: return p0 < p1;
+        case PRIOR_NORMAL: case PRIOR_LOGNORMAL: case PRIOR_CAUCHY: case PRIOR_LAPLACE: return p1 > 0.0 && p0 == p0;
+        case PRIOR_EXPONENTIAL: return p0 > 0.0;
+        case PRIOR_GAMMA: case PRIOR_BETA: case PRIOR_WEIBULL: case PRIOR_INVGAMMA: return p0 > 0.0 && p1 > 0.0;
+        default: return false;
+    }
+}
 
 inline void prior_prepare(PriorSpec& p) {
     for (int i = 0; i < p.n; ++i) {
@@ -42,6 +56,9 @@ inline void prior_prepare(PriorSpec& p) {
             case PRIOR_EXPONENTIAL: p.c[i] = det_log(p.p0[i]); break;
             case PRIOR_GAMMA: p.c[i] = det_lgamma(p.p0[i]) + p.p0[i] * det_log(p.p1[i]); break;
             case PRIOR_BETA: p.c[i] = (det_lgamma(p.p0[i]) + det_lgamma(p.p1[i])) - det_lgamma(p.p0[i] + p.p1[i]); break;
+            case PRIOR_LAPLACE: p.c[i] = det_log(2.0 * p.p1[i]); break;
+            case PRIOR_WEIBULL: p.c[i] = det_log(p.p0[i] / p.p1[i]); break;
+            case PRIOR_INVGAMMA: p.c[i] = det_lgamma(p.p0[i]) - p.p0[i] * det_log(p.p1[i]); break;
             default: p.c[i] = det_log(p.p1[i]); break;
         }
     }
@@ -68,6 +85,22 @@ SABC_HD double prior_logpdf1(int kind, double p0, double p1, double c, double x)
         const double t0 = a1 == 0.0 ? 0.0 : a1 * det_log(x);
         const double t1 = b1 == 0.0 ? 0.0 : b1 * det_log(1.0 - x);
         return (t0 + t1) - c;
+    }
+    if (kind == PRIOR_CAUCHY) {                              // -(log1p(z^2) + log(pi) + log(sigma))
+        const double z = (x - p0) / p1;
+        return -((det_log(1.0 + z * z) + 0x1.250d048e7a1bdp+0) + c);
+    }
+    if (kind == PRIOR_LAPLACE) return -(fabs(x - p0) / p1 + c);
+    if (kind == PRIOR_WEIBULL) {                             // log(alpha/theta) + (alpha-1) log z - z^alpha, z = x/theta
+        if (!(x >= 0.0)) return -dinf();
+        const double lz = det_log(x / p1);
+        const double a1 = p0 - 1.0;
+        const double t = a1 == 0.0 ? 0.0 : a1 * lz;
+        return (c + t) - det_exp(p0 * lz);
+    }
+    if (kind == PRIOR_INVGAMMA) {                            // alpha log(theta) - lgamma(alpha) - (alpha+1) log x - theta/x
+        if (!(x > 0.0)) return -dinf();
+        return (-((p0 + 1.0) * det_log(x)) - p1 / x) - c;
     }
     if (!(x > 0.0)) return -dinf();                         // LogNormal
     const double lx = det_log(x);
@@ -128,6 +161,18 @@ SABC_HD void prior_rand(const PriorSpec& p, uint64_t seed, uint32_t particle, do
                 th[c] = g1 / (g1 + g2);
                 break;
             }
+            case PRIOR_CAUCHY: {                              // quantile: mu + sigma tan(pi (u - 1/2)) = mu - sigma cos(pi u) / sin(pi u)
+                double sn, cs; det_sincos2pi(0.5 * u53_mid(w.a), sn, cs);
+                th[c] = p.p0[c] - p.p1[c] * (cs / sn);
+                break;
+            }
+            case PRIOR_LAPLACE: {                             // quantile: mu + theta log(2u) below 1/2, mu - theta log(2(1-u)) above
+                const double u = u53_mid(w.a);
+                th[c] = u < 0.5 ? p.p0[c] + p.p1[c] * det_log(2.0 * u) : p.p0[c] - p.p1[c] * det_log(2.0 * (1.0 - u));
+                break;
+            }
+            case PRIOR_WEIBULL: th[c] = p.p1[c] * det_exp(det_log(-det_log(u53_open0(w.a))) / p.p0[c]); break;   // theta E^(1/alpha), E ~ Exp(1)
+            case PRIOR_INVGAMMA: th[c] = p.p1[c] / gamma_std(p.p0[c], st, (uint32_t)c, 0u); break;
             default: normal_pair(w, z0, z1); th[c] = det_exp(p.p0[c] + p.p1[c] * z0); break;
         }
     }

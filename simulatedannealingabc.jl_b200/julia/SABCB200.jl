@@ -9,7 +9,7 @@ module SABCB200
 using SimulatedAnnealingABC
 import SimulatedAnnealingABC: sabc, update_population!, SABCresult, SABCstate, Proposal,
                               DifferentialEvolution, StretchMove, RandomWalk
-using Distributions: Distribution, Uniform, Normal, Exponential, LogNormal, Gamma, Beta, Product, params
+using Distributions: Distribution, Uniform, Normal, Exponential, LogNormal, Gamma, Beta, Cauchy, Laplace, Weibull, InverseGamma, Product, params
 
 const libsabc = get(ENV, "SABC_B200_LIB", joinpath(@__DIR__, "..", "libsabc_b200.so"))
 
@@ -44,9 +44,10 @@ sir_tauleap(obs_total, obs_peak, obs_tpeak; pop=1e5, n_steps=50, τ=1.0) =
     DeviceModel("sir_tauleap", 4, 3, [pop, n_steps, τ, obs_total, obs_peak, obs_tpeak])
 
 # ---- plug-in encodings ----
-prior_components(p::Union{Uniform,Normal,Exponential,LogNormal,Gamma,Beta}) = [p]
+prior_components(p::Union{Uniform,Normal,Exponential,LogNormal,Gamma,Beta,Cauchy,Laplace,Weibull,InverseGamma}) = [p]
 prior_components(p::Product) = collect(p.v)
 prior_kind(::Uniform) = Int32(0); prior_kind(::Normal) = Int32(1); prior_kind(::Exponential) = Int32(2); prior_kind(::LogNormal) = Int32(3); prior_kind(::Gamma) = Int32(4); prior_kind(::Beta) = Int32(5)
+prior_kind(::Cauchy) = Int32(6); prior_kind(::Laplace) = Int32(7); prior_kind(::Weibull) = Int32(8); prior_kind(::InverseGamma) = Int32(9)
 prior_params(c) = (p = params(c); length(p) == 2 ? (p[1], p[2]) : (p[1], 0.0))
 proposal_code(p::DifferentialEvolution) = (Int32(0), (p.γ0, p.σ_gamma))
 proposal_code(p::StretchMove) = (Int32(1), (p.a, 0.0))

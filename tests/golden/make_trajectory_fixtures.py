@@ -27,6 +27,8 @@ CASES = [  # name, N, updates, algorithm, proposal
     ("sir_tauleap", 1024, 12, "single_eps", "de"),
     ("sir_gillespie_s3", 2000, 20, "multi_eps", "de"),
     ("gauss_sample_d2s2_gambeta", 1000, 20, "multi_eps", "de"),   # Gamma x Beta prior
+    ("gauss_sample_d2s2_laplinvg", 1000, 15, "single_eps", "de"), # Laplace x InverseGamma prior
+    ("gauss_sample_d2s2_cauweib", 1000, 15, "multi_eps", "stretch"),  # Cauchy x Weibull prior
 ]
 
 

@@ -30,6 +30,10 @@ def model_cases():
                                     sb.product_distribution([sb.LogNormal(0.5, 0.8), sb.Exponential(1.5)])),
         "gauss_sample_d2s2_gambeta": (m.gauss_sample(10, 2.0, 42.5, n_para=2, second_is_sum=True),
                                       sb.product_distribution([sb.Gamma(2.5, 0.8), sb.Beta(0.7, 3.0)])),
+        "gauss_sample_d2s2_laplinvg": (m.gauss_sample(10, 2.0, 42.5, n_para=2, second_is_sum=True),
+                                       sb.product_distribution([sb.Laplace(1.0, 1.5), sb.InverseGamma(3.0, 2.0)])),
+        "gauss_sample_d2s2_cauweib": (m.gauss_sample(10, 2.0, 42.5, n_para=2, second_is_sum=True),
+                                      sb.product_distribution([sb.Cauchy(1.0, 0.5), sb.Weibull(1.7, 1.2)])),
         "logistic": (m.logistic(obs_logistic()), sb.product_distribution([sb.Uniform(0, 1), sb.Uniform(50, 500), sb.Uniform(0, 0.5)])),
         "sir_gillespie_s3": (m.sir_gillespie(83.0, 24.0, 41.7), sb.product_distribution([sb.Uniform(0.1, 1), sb.Uniform(0.05, 0.5)])),
         "sir_gillespie_s1": (m.sir_gillespie(83.0, 24.0, 41.7, single_stat=True), sb.product_distribution([sb.Uniform(0.1, 1), sb.Uniform(0.05, 0.5)])),

@@ -52,11 +52,13 @@ int main(int argc, char** argv) {
     }
     // priors: every family, draws and log-densities (also off the support)
     const int n_prior = 20000;
-    const int32_t kinds[3][6] = {{4, 5, 0, 1, 2, 3}, {5, 4, 4, 5, 4, 5}, {4, 4, 5, 5, 1, 0}};
-    const double pars[3][12] = {{2.5, 0.8, 0.7, 3.0, -1.0, 3.0, 0.5, 2.0, 1.5, 0.0, 0.5, 0.8},
+    const int32_t kinds[5][6] = {{4, 5, 0, 1, 2, 3}, {5, 4, 4, 5, 4, 5}, {4, 4, 5, 5, 1, 0}, {6, 7, 8, 9, 8, 9}, {9, 8, 7, 6, 8, 9}};
+    const double pars[5][12] = {{2.5, 0.8, 0.7, 3.0, -1.0, 3.0, 0.5, 2.0, 1.5, 0.0, 0.5, 0.8},
                                 {4.0, 2.0, 0.4, 1.5, 1.0, 3.0, 1.0, 1.0, 30.0, 0.01, 0.05, 0.05},
-                                {0.05, 1.0, 100.0, 2.0, 0.5, 0.5, 50.0, 60.0, 0.0, 1.0, 0.0, 1.0}};
-    for (int set = 0; set < 3; ++set) {
+                                {0.05, 1.0, 100.0, 2.0, 0.5, 0.5, 50.0, 60.0, 0.0, 1.0, 0.0, 1.0},
+                                {0.5, 2.0, -1.0, 0.7, 1.7, 2.5, 3.0, 2.0, 0.6, 1.0, 0.5, 0.1},
+                                {20.0, 5.0, 1.0, 3.0, 0.0, 10.0, -3.0, 0.01, 5.0, 0.2, 1.0, 1.0}};
+    for (int set = 0; set < 5; ++set) {
         PriorSpec ps{};
         ps.n = 6;
         for (int c = 0; c < 6; ++c) { ps.kind[c] = kinds[set][c]; ps.p0[c] = pars[set][2 * c]; ps.p1[c] = pars[set][2 * c + 1]; }
@@ -75,6 +77,6 @@ int main(int argc, char** argv) {
             if (memcmp(&lp, &lo, 8) != 0 && !(lp != lp && lo != lo)) { if (bad < 10) printf("prior_logpdf mismatch set %d particle %d: %.17g vs %.17g\n", set, i, lp, lo); bad++; }
         }
     }
-    printf("%d poisson draws, %d sir simulations, %d x 3 prior draws, %ld mismatches\n", n_draw, n_sim, n_prior, bad);
+    printf("%d poisson draws, %d sir simulations, %d x 5 prior draws, %ld mismatches\n", n_draw, n_sim, n_prior, bad);
     return bad != 0;
 }

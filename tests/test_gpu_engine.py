@@ -40,7 +40,7 @@ def test_c1_gauss_mean_trajectory(gpu):
 
 
 @pytest.mark.parametrize("name", ["gauss_sample_d1s1", "gauss_sample_d2s1", "gauss_sample_d1s2", "gauss_sample_d2s2", "logistic", "sir_tauleap",
-                                  "sir_gillespie_s3", "sir_gillespie_s1", "gauss_sample_d2s2_lnexp", "gauss_sample_d2s2_gambeta"])
+                                  "sir_gillespie_s3", "sir_gillespie_s1", "gauss_sample_d2s2_lnexp", "gauss_sample_d2s2_gambeta", "gauss_sample_d2s2_laplinvg", "gauss_sample_d2s2_cauweib"])
 @pytest.mark.parametrize("algorithm", ["single_eps", "multi_eps"])
 def test_models_trajectory(gpu, name, algorithm):
     model, prior = model_cases()[name]

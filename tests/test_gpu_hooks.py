@@ -227,6 +227,21 @@ def test_prior_logpdf_gamma_beta(gpu):
         assert np.all(np.isneginf(lp[out]))
 
 
+def test_prior_logpdf_more_families(gpu):
+    """Cauchy, Laplace, Weibull, InverseGamma: device == oracle bit for bit (also off the support and at the edges)."""
+    rng = np.random.default_rng(8)
+    kind = np.array([6, 7, 8, 9], dtype=np.int32)
+    for par in ([0.5, 2.0, -1.0, 0.7, 1.7, 2.5, 3.0, 2.0], [0.0, 1.0, 0.0, 1.0, 1.0, 3.0, 0.5, 0.1], [-3.0, 0.01, 2.0, 5.0, 0.6, 1.0, 20.0, 5.0]):
+        par = np.array(par)
+        th = np.asfortranarray(np.column_stack([rng.normal(0, 5, 4000), rng.normal(0, 3, 4000), rng.uniform(-1, 8, 4000), rng.uniform(-1, 8, 4000)]))
+        th[:3] = [[0.0, 0.0, 0.0, 0.0], [1.0, -1.0, 0.0, 1.0], [0.5, 0.0, 1.0, 0.0]]
+        lp = np.zeros(4000)
+        L.check(L.lib().sabc_prior_logpdf(4, ptr(kind), ptr(par), ptr(th), 4000, ptr(lp)))
+        want = np.array([ob.lib().orc_prior_logpdf(4, ob.p(kind), ob.p(par), ob.p(np.ascontiguousarray(th[i]))) for i in range(4000)])
+        assert np.array_equal(lp, want, equal_nan=True)
+        assert np.all(np.isneginf(lp[(th[:, 2] < 0) | (th[:, 3] <= 0)]))
+
+
 @pytest.mark.parametrize("name", list(model_cases().keys()))
 def test_model_simulate_bit_exact(gpu, name):
     model, prior = model_cases()[name]
@@ -239,6 +254,10 @@ def test_model_simulate_bit_exact(gpu, name):
         if isinstance(c, sb.Exponential): return rng.exponential(c.theta, n)
         if isinstance(c, sb.Gamma): return rng.gamma(c.alpha, c.theta, n)
         if isinstance(c, sb.Beta): return rng.beta(c.alpha, c.beta, n)
+        if isinstance(c, sb.Cauchy): return c.mu + c.sigma * rng.standard_cauchy(n)
+        if isinstance(c, sb.Laplace): return rng.laplace(c.mu, c.theta, n)
+        if isinstance(c, sb.Weibull): return c.theta * rng.weibull(c.alpha, n)
+        if isinstance(c, sb.InverseGamma): return c.theta / rng.gamma(c.alpha, 1.0, n)
         return rng.lognormal(c.mu, c.sigma, n)
     th = np.column_stack([draw(c) for c in comps])
     rho = model.simulate(th, seed=123, particle_base=1000, sweep=7)

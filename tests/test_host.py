@@ -159,7 +159,8 @@ def test_exchange_plan_is_consistent():
 def test_prior_constructors_validate_like_distributions_jl():
     """Distributions.jl throws DomainError for invalid parameters at construction; the mirror raises ValueError."""
     for bad in (lambda: sb.Uniform(1.0, 1.0), lambda: sb.Normal(0.0, 0.0), lambda: sb.Exponential(-1.0), lambda: sb.LogNormal(0.0, -1.0),
-                lambda: sb.Gamma(0.0, 1.0), lambda: sb.Gamma(1.0, -2.0), lambda: sb.Beta(-1.0, 1.0), lambda: sb.Beta(1.0, 0.0)):
+                lambda: sb.Gamma(0.0, 1.0), lambda: sb.Gamma(1.0, -2.0), lambda: sb.Beta(-1.0, 1.0), lambda: sb.Beta(1.0, 0.0),
+                lambda: sb.Cauchy(0.0, 0.0), lambda: sb.Laplace(0.0, -1.0), lambda: sb.Weibull(0.0, 1.0), lambda: sb.InverseGamma(1.0, 0.0)):
         with pytest.raises(ValueError):
             bad()
     p = sb.product_distribution([sb.Gamma(2.0, 0.5), sb.Beta(2.0, 3.0), sb.Uniform(0, 1)])

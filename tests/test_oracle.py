@@ -257,3 +257,33 @@ def test_gamma_beta_priors():
         for i in range(n):
             L.orc_prior_rand(1, ob.p(kk), ob.p(pp), 99, i, ob.p(out)); x[i] = out[0]
         assert stats.kstest(x, dist.cdf).pvalue > 1e-3, (kind, par)
+
+
+def test_cauchy_laplace_weibull_inversegamma_priors():
+    """Log-densities against scipy (Distributions.jl parametrisations: Weibull(shape, scale), InverseGamma(shape, scale)),
+    quantile / Marsaglia-Tsang draws against the exact distributions (KS)."""
+    from scipy import stats
+    L = ob.lib()
+    rng = np.random.default_rng(3)
+    cases = [(6, (0.5, 2.0), stats.cauchy(0.5, 2.0)), (7, (-1.0, 0.7), stats.laplace(-1.0, 0.7)),
+             (8, (1.7, 2.5), stats.weibull_min(1.7, scale=2.5)), (8, (0.6, 1.0), stats.weibull_min(0.6, scale=1.0)),
+             (8, (1.0, 3.0), stats.weibull_min(1.0, scale=3.0)), (9, (3.0, 2.0), stats.invgamma(3.0, scale=2.0)),
+             (9, (0.5, 0.1), stats.invgamma(0.5, scale=0.1))]
+    for kind, par, dist in cases:
+        kk = np.array([kind], dtype=np.int32); pp = np.array(par)
+        xs = np.concatenate([dist.rvs(500, random_state=rng), rng.uniform(-3, 10, 300)])
+        got = np.array([L.orc_prior_logpdf(1, ob.p(kk), ob.p(pp), ob.p(np.array([x]))) for x in xs])
+        ref = dist.logpdf(xs)
+        fin = np.isfinite(ref)
+        assert np.allclose(got[fin], ref[fin], rtol=1e-11, atol=1e-11), (kind, par)
+        assert np.all(np.isneginf(got[~fin])), (kind, par)
+        n = 20000; out = np.zeros(1); x = np.empty(n)
+        for i in range(n):
+            L.orc_prior_rand(1, ob.p(kk), ob.p(pp), 7, i, ob.p(out)); x[i] = out[0]
+        assert np.all(np.isfinite(x)) and stats.kstest(x, dist.cdf).pvalue > 1e-3, (kind, par)
+    # edges: Weibull at 0 follows xlogy (alpha = 1: log(1/theta); alpha > 1: -Inf; alpha < 1: +Inf), InverseGamma at 0 is -Inf
+    k8 = np.array([8], dtype=np.int32)
+    lp = lambda a, t, x: L.orc_prior_logpdf(1, ob.p(k8), ob.p(np.array([a, t])), ob.p(np.array([x])))
+    assert abs(lp(1.0, 2.0, 0.0) + np.log(2.0)) < 1e-14 and lp(2.0, 1.0, 0.0) == -np.inf and lp(0.5, 1.0, 0.0) == np.inf
+    k9 = np.array([9], dtype=np.int32)
+    assert L.orc_prior_logpdf(1, ob.p(k9), ob.p(np.array([2.0, 1.0])), ob.p(np.array([0.0]))) == -np.inf
