@@ -74,6 +74,34 @@ __global__ void k_ptrs_filter_check(const double* lam, int n_lam, int64_t attemp
     atomicMax(ratio_bits + 0, (unsigned long long)__double_as_longlong(r1));   // non-negative doubles order like integers
     atomicMax(ratio_bits + 1, (unsigned long long)__double_as_longlong(r2));
 }
+#if defined(SABC_EXPERIMENTAL_PTRS2)
+// experimental attempt (ptrs2_experimental.cuh) against the product attempt on `attempts` candidates:
+// counts = {attempts, undecided by the approximate candidate, acceptance tests reached, undecided by filter 2, wrong}
+__global__ void k_ptrs2_check(const double* lam, int n_lam, int64_t attempts, uint64_t seed, unsigned long long* counts) {
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < attempts; i += (int64_t)gridDim.x * blockDim.x) {
+        const double l = lam[i % n_lam];
+        Stream st(seed, (uint32_t)i, (uint64_t)(i >> 32), KIND_MODEL);
+        const U64x2 w = st.draw();
+        double kf0, num = 0.0, den = 0.0, kf1;
+        int s0 = ptrs_candidate(l, w, kf0, num, den);
+        if (s0 == 2) s0 = (int)ptrs_exact(l, kf0, num, den);
+        float numf = 0.0f, denf = 0.0f;
+        int s1 = ptrs_candidate_mufu(l, w, kf1, numf, denf);
+        c[0]++;
+        if (s1 == 3) { c[1]++; continue; }
+        if (s1 == 2) {
+            c[2]++;
+            float T, E;
+            const int dec = ptrs_filter_mufu2(l, kf1, numf, denf, T, E);
+            if (dec == 0) { c[3]++; if (kf1 != kf0) c[4]++; continue; }
+            s1 = dec > 0;
+        }
+        if (s1 != s0 || (s0 == 1 && kf1 != kf0)) c[4]++;
+    }
+    for (int j = 0; j < 5; ++j) if (c[j]) atomicAdd(counts + j, c[j]);
+}
+#endif
 __global__ void k_accept(int64_t m, int s, const double* uo, const double* un, const double* eps, int n_eps, const double* dlp,
                          const double* lf, const double* U, uint8_t* acc) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
@@ -188,6 +216,21 @@ int sabc_ptrs_filter_check(const double* lam, int32_t n_lam, int64_t attempts, u
     for (int j = 0; j < 2; ++j) { double r; memcpy(&r, &h[5 + j], 8); ratio_out[j] = r; }
     return 0;
 }
+
+#if defined(SABC_EXPERIMENTAL_PTRS2)
+int sabc_ptrs2_check(const double* lam, int32_t n_lam, int64_t attempts, uint64_t seed, int64_t counts_out[5]) {
+    if (!lam || n_lam < 1 || attempts < 0 || !counts_out) return set_error(SABC_ERR_INVALID, "bad argument");
+    DevBuf<double> dl; DevBuf<unsigned long long> dc;
+    SABC_TRY(upload(dl, lam, (size_t)n_lam)); SABC_CUDA(dc.alloc(5));
+    SABC_CUDA(cudaMemset(dc.p, 0, 5 * sizeof(unsigned long long)));
+    k_ptrs2_check<<<148 * 8, 256>>>(dl.p, n_lam, attempts, seed, dc.p);
+    SABC_CUDA(cudaGetLastError());
+    unsigned long long h[5];
+    SABC_TRY(download(h, dc, 5));
+    for (int j = 0; j < 5; ++j) counts_out[j] = (int64_t)h[j];
+    return 0;
+}
+#endif
 
 // build_cdf(::AbstractVector)  src/cdf_estimators.jl:23-44
 int sabc_ecdf_build(const double* dist, int64_t n, double* knots_out, int64_t* L) {

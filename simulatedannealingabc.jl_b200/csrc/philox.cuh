@@ -246,6 +246,12 @@ SABC_HD bool ptrs_exact(double lam, double kf, double num, double den) {
     return lhs <= rhs;
 }
 
+#if defined(SABC_EXPERIMENTAL_PTRS2) && defined(__CUDACC__)
+}  // namespace sabc
+#include "ptrs2_experimental.cuh"   // not in the product build: see the header of that file
+namespace sabc {
+#endif
+
 // Poisson(lam): one-uniform sequential-search inversion below 10, PTRS above, with the acceptance tests
 // rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one Philox block (none when
 // lam <= 0) and either returns a count or rejects; this is the unit the SIR kernel interleaves across lanes so that a
@@ -268,6 +274,12 @@ SABC_HD bool poisson_attempt_d(double lam, Stream& st, double& k_out) {
         return true;
     }
     double kf, num = 0.0, den = 0.0;
+#if defined(SABC_EXPERIMENTAL_PTRS2) && defined(__CUDA_ARCH__)
+    {
+        const int s2 = ptrs_attempt2(lam, w, kf);
+        if (s2 != 3) { if (s2 == 1) k_out = kf; return s2 == 1; }
+    }
+#endif
     int s = ptrs_candidate(lam, w, kf, num, den);
     if (s == 2) {
 #if !defined(SABC_NO_PTRS_FILTER)
