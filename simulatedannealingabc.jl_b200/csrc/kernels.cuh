@@ -160,6 +160,16 @@ struct PopView {                 // structure-of-arrays particle state of one GP
     int64_t ld;
 };
 
+// -DSABC_EXPERIMENTAL_RK_ALL (NOT in the product build, never run on a GPU): the fused and the propose kernels also take the
+// Philox round keys from the parameter block, as the simulation kernel of the split path does
+#if defined(SABC_EXPERIMENTAL_RK_ALL)
+#define SABC_RK_ALL(a) ((a).rk.k)
+#define SABC_GRID_CONSTANT __grid_constant__
+#else
+#define SABC_RK_ALL(a) nullptr
+#define SABC_GRID_CONSTANT
+#endif
+
 struct UpdateArgs {
     PopView pop;
     int64_t act_off, act_n, ina_off, ina_n;   // active / inactive half (local indices)
@@ -262,7 +272,7 @@ SABC_D void stage_ecdf_top(const EcdfStat* ecdf, int S, double* s_top) {
 // the partial reductions the ε update, the resampling weights and the history need.
 // ------------------------------------------------------------------------------------------------
 template <class M, int PROP>
-__global__ void __launch_bounds__(CHUNK) update_half_kernel(const UpdateArgs a) {
+__global__ void __launch_bounds__(CHUNK) update_half_kernel(const SABC_GRID_CONSTANT UpdateArgs a) {
     constexpr int D = M::D, S = M::S;
     extern __shared__ __align__(128) double s_top[];
     __shared__ unsigned long long s_acc[2 * S + 1];
@@ -294,13 +304,13 @@ __global__ void __launch_bounds__(CHUNK) update_half_kernel(const UpdateArgs a) 
             double th[D], thp[D], lf;
 #pragma unroll
             for (int c = 0; c < D; ++c) th[c] = a.pop.theta[c * ld + gi];
-            const CtrlWords cw = ctrl_words(a.seed, pid, sweep);
+            const CtrlWords cw = ctrl_words(a.seed, pid, sweep, SABC_RK_ALL(a));
             if (PROP == PROP_DE) propose_de<D>(th, P, a.ina_n, a.prop0, a.prop1, cw, thp, lf);
             else if (PROP == PROP_STRETCH) propose_stretch<D>(th, P, a.ina_n, a.prop0, cw, thp, lf);
             else propose_rw<D>(th, s_chol, a.seed, pid, sweep, thp, lf);
             const double lpp = prior_logpdf<D>(a.prior, thp);
             if (lpp > -dinf()) {                                       // :314 (no simulation outside the support)
-                Stream st(a.seed, pid, sweep, KIND_MODEL);
+                Stream st(a.seed, pid, sweep, KIND_MODEL, SABC_RK_ALL(a));
                 M::sim(thp, a.mp, st, rp);                              // :315
                 double Ssum = 0.0;
 #pragma unroll
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(CHUNK) update_half_kernel(const UpdateArgs a) 
                     Ssum = (j == 0) ? t : Ssum + t;
                 }
                 const double Lacc = ((lpp - a.pop.lp[gi]) + Ssum) + lf; // :318-319
-                acc = det_log(u53(cw.D)) < Lacc;                        // :324
+                acc = log_u_less(u53(cw.D), Lacc);                      // :324
             }
             if (acc) {                                                  // :325-328
 #pragma unroll
@@ -357,7 +367,7 @@ __global__ void __launch_bounds__(CHUNK) update_half_kernel(const UpdateArgs a) 
 // Results are identical to the fused kernel: every particle uses the same Philox streams and arithmetic.
 // ------------------------------------------------------------------------------------------------
 template <class M, int PROP>
-__global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, const SplitScratch w) {
+__global__ void __launch_bounds__(CHUNK) propose_kernel(const SABC_GRID_CONSTANT UpdateArgs a, const SplitScratch w) {
     constexpr int D = M::D;
     __shared__ double s_chol[PROP == PROP_RW ? D * D : 1];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -376,7 +386,7 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, cons
             double th[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) th[c] = a.pop.theta[c * ld + gi];
-            const CtrlWords cw = ctrl_words(a.seed, pid, sweep);
+            const CtrlWords cw = ctrl_words(a.seed, pid, sweep, SABC_RK_ALL(a));
             if (PROP == PROP_DE) propose_de<D>(th, P, a.ina_n, a.prop0, a.prop1, cw, thp, lf);
             else if (PROP == PROP_STRETCH) propose_stretch<D>(th, P, a.ina_n, a.prop0, cw, thp, lf);
             else propose_rw<D>(th, s_chol, a.seed, pid, sweep, thp, lf);
@@ -443,7 +453,7 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
             const double lpp = w.lp[q];
             const double Lacc = ((lpp - a.pop.lp[gi]) + Ssum) + w.lf[q]; // :318-319
             const uint64_t wD = Stream(a.seed, pid, sweep, KIND_CTRL).block(1).b;   // accept uniform: word D of the control stream
-            if (det_log(u53(wD)) < Lacc) {                              // :324-328
+            if (log_u_less(u53(wD), Lacc)) {                            // :324-328
 #pragma unroll
                 for (int c = 0; c < D; ++c) a.pop.theta[c * ld + gi] = thp[c];
 #pragma unroll

@@ -183,8 +183,8 @@ SABC_HD void prior_rand(const PriorSpec& p, uint64_t seed, uint32_t particle, do
 // ------------------------------------------------------------------------------------------------
 struct CtrlWords { uint64_t A, B, C, D; };   // blocks 0 and 1 of the control stream
 
-SABC_HD CtrlWords ctrl_words(uint64_t seed, uint32_t particle, uint64_t sweep) {
-    const Stream st(seed, particle, sweep, KIND_CTRL);
+SABC_HD CtrlWords ctrl_words(uint64_t seed, uint32_t particle, uint64_t sweep, const uint32_t* rk = nullptr) {
+    const Stream st(seed, particle, sweep, KIND_CTRL, rk);
     const U64x2 b0 = st.block(0), b1 = st.block(1);
     return CtrlWords{b0.a, b0.b, b1.a, b1.b};
 }
@@ -260,6 +260,21 @@ SABC_HD int64_t count_less(const double* a, int64_t n, double x) {
 }
 
 #if defined(__CUDACC__)
+// the Metropolis test log(U) < L  (src/SimulatedAnnealingABC.jl:324).  -DSABC_EXPERIMENTAL_ACCEPT_FILTER (NOT in the product
+// build, never run on a GPU, see DEVELOPMENT.md) decides it with one MUFU.LG2 when |log U - L| exceeds the error of that
+// estimate (float(U): 6e-8, lg2.approx: 2 ulp of |log2 U| <= 60 -> 1e-5, one product: 3e-6; bound used 4e-5) and evaluates
+// det_log only for the ~1e-4 of the particles inside the band, so the decision -- and the trajectory -- is unchanged.
+SABC_D bool log_u_less(double U, double L) {
+#if defined(SABC_EXPERIMENTAL_ACCEPT_FILTER)
+    if (U > 0x1p-60) {
+        const double l = (double)__fmul_rn(0.693147180559945f, mufu_lg2(__double2float_rn(U)));
+        if (l < L - 4e-5) return true;
+        if (l > L + 4e-5) return false;
+    }
+#endif
+    return det_log(U) < L;
+}
+
 // same count over an array staged in shared memory, 8-ary: each round reads 7 pivots at once, so a 2048-entry level
 // costs 4 dependent shared-memory latencies instead of 11
 SABC_D int count_less_smem(const double* a, int n, double x) {
@@ -281,6 +296,14 @@ SABC_D int count_less_smem(const double* a, int n, double x) {
 // Fetching the whole line at once (8 x 16 B, one latency) was measured 1.7x SLOWER on C5: the kernel is bound by
 // L1/LSU wavefronts of scattered accesses (63 % of peak, profiles/r1_c5_update_half_v0_ncu.txt), not by the probe chain.
 SABC_D int count_less16(const double* node, double x) {
+#if defined(SABC_EXPERIMENTAL_NODE2)
+    // NOT in the product build, never run on a GPU: the same count in two dependent rounds instead of five -- the quarter
+    // from entries 3, 7, 11, then the four entries of that quarter (sorted: the entries below x form a prefix).  Seven loads
+    // of one 128-byte line instead of five; the long-scoreboard stall of the Gaussian kernels sits on this chain.
+    const int qd = ((__ldg(node + 3) < x) ? 1 : 0) + ((__ldg(node + 7) < x) ? 1 : 0) + ((__ldg(node + 11) < x) ? 1 : 0);
+    const double* qn = node + 4 * qd;
+    return 4 * qd + ((__ldg(qn) < x) ? 1 : 0) + ((__ldg(qn + 1) < x) ? 1 : 0) + ((__ldg(qn + 2) < x) ? 1 : 0) + ((__ldg(qn + 3) < x) ? 1 : 0);
+#endif
     int lo = 0;
 #pragma unroll
     for (int step = 8; step >= 1; step >>= 1) lo += (__ldg(node + lo + step - 1) < x) ? step : 0;
