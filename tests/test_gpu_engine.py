@@ -308,3 +308,20 @@ def test_full_size_properties(gpu, name, N, alg):
     assert np.allclose(uh[-1], u.mean(axis=0), rtol=1e-12, atol=0)
     assert np.allclose(rh[-1], rho.mean(axis=0), rtol=1e-9, atol=0)
     assert np.all(np.diff(eh[:, 0]) < 0) and np.all(eps > 0)            # eps anneals monotonically in these runs
+
+
+@pytest.mark.parametrize("name,N,alg", [("gauss_sample_d2s2", 100_000, "multi_eps"),        # C2
+                                        ("logistic", 1_000_000, "single_eps"),              # C3 (split path, s = 20, "hybrid")
+                                        ("sir_tauleap", 1_250_000, "single_eps"),           # C4 per-GPU slice (split path, 625 000-item work list)
+                                        ("gauss_mean", 10_000_000, "single_eps")])          # C5 (deepest ECDF index, many scan tiles)
+def test_full_size_parity_vs_oracle(gpu, name, N, alg):
+    """BASELINE.json's configurations at their OWN sizes against the oracle, bit for bit: initialization (prior sample, global sort,
+    ECDF knots, transform, first resampling, eps_0) + 3 population updates with resamplings in between.  The oracle runs on all host
+    threads (a few seconds per case)."""
+    import os
+    ob.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))
+    model, prior = model_cases()[name]
+    eng, orc = run_pair(model, prior, N, 3, algorithm=alg, resample=N // 8)
+    cnt = eng.get_state()[1]
+    assert cnt[0] == 4 * N and cnt[3] == 3 and cnt[2] >= 2, cnt           # at least one resampling after the initial one
+    eng.close(); orc.close()
