@@ -10,6 +10,7 @@
 
 struct Ar1Model {
     static constexpr int D = 2, S = 2;
+    static constexpr int FUSED_MIN_BLOCKS = 1; // resident CTAs per SM requested for the fused kernel
     static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel (split path)
     static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[2], const sabc::ModelPar& mp, sabc::Stream& st, double (&rho)[2]) {
@@ -17,7 +18,7 @@ struct Ar1Model {
         double x = 0.0, s1 = 0.0, s2 = 0.0, sx = 0.0;
         for (int t = 0; t < T; t += 2) {
             double z[2];
-            sabc::normal_pair(st.draw(), z[0], z[1]);          // one Philox block -> two normals
+            sabc::normal2(st, z[0], z[1]);                     // one Philox block -> two normals (ziggurat)
             for (int h = 0; h < 2 && t + h < T; ++h) {
                 const double xn = th[0] * x + th[1] * z[h];
                 s1 = s1 + xn * x;                                // lag-1 cross product

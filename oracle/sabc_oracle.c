@@ -183,7 +183,7 @@ static inline double u53_open0(uint64_t x) { return (double)((x >> 11) + 1) * 0x
 static inline double u53_mid(uint64_t x) { return ((double)(x >> 11) + 0.5) * 0x1p-53; }   /* (0,1)  */
 static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 
-/* Box-Muller pair from one block (53-bit uniforms) -- stands in for randn() */
+/* Box-Muller pair from one block (53-bit uniforms): the normal behind the PRIOR draws (initialization) */
 void orc_normal_pair(uint64_t a, uint64_t b, double* z0, double* z1) {
     double u1 = u53_open0(a), u2 = u53(b);
     double r = sqrt(-2.0 * orc_log(u1));
@@ -191,14 +191,51 @@ void orc_normal_pair(uint64_t a, uint64_t b, double* z0, double* z1) {
     orc_sincos2pi(u2, &sn, &cs);
     *z0 = r * cs; *z1 = r * sn;
 }
-/* cheaper normal from one 64-bit word (two 32-bit uniforms); used for the DE gamma jitter */
-static double normal32(uint64_t c) {
-    double u1 = (double)((c & 0xffffffffULL) + 1) * 0x1p-32;
-    double u2 = (double)(c >> 32) * 0x1p-32;
-    double r = sqrt(-2.0 * orc_log(u1));
-    double sn, cs;
-    orc_sincos2pi(u2, &sn, &cs);
-    return r * cs;
+/* randn() on the hot path (src/proposals.jl:42,54,110 and the models' noise; Julia's randn() is a ziggurat as well):
+   256-layer ziggurat (Marsaglia & Tsang 2000) on ONE 64-bit word -- spec DESIGN.md section 3.3:
+     bits 0..7 layer i, bit 8 sign, bits 11..63 the 53-bit integer m; x = m * W[i]; m < K[i] -> +-x (98.5 %).
+   Otherwise one extra block e of the same stream: layer 0 -> tail beyond R (xx = -log(U(e.a))/R, yy = -log(U(e.b)), accept R + xx
+   when 2 yy > xx^2, else the next block); layer >= 1 -> wedge (accept x when F[i] + U(e.a)(F[i+1] - F[i]) < exp(-x^2/2), else start
+   again with the word e.b).  Tables: tools/gen_ziggurat.py. */
+#include "zig_tables.inc"
+static double zig_normal(uint64_t w, stream_t* st) {
+    for (;;) {
+        uint32_t i = (uint32_t)w & 255u;
+        uint64_t m = w >> 11;
+        int neg = (int)((w >> 8) & 1u);
+        double x = (double)m * ZIG_KW[i].w;
+        if (m < ZIG_KW[i].k) return neg ? -x : x;
+        uint64_t ea, eb;
+        stream_next(st, &ea, &eb);
+        if (i == 0) {
+            for (;;) {
+                double xx = (-orc_log(u53_open0(ea))) * ZIG_INV_R;
+                double yy = -orc_log(u53_open0(eb));
+                if (yy + yy > xx * xx) return neg ? -(ZIG_R + xx) : ZIG_R + xx;
+                stream_next(st, &ea, &eb);
+            }
+        }
+        double y = ZIG_F[i] + u53(ea) * (ZIG_F[i + 1] - ZIG_F[i]);
+        if (y < orc_exp((-0.5 * x) * x)) return neg ? -x : x;
+        w = eb;
+    }
+}
+/* two / one normals from the next block of a stream */
+static void normal2(stream_t* st, double* z0, double* z1) {
+    uint64_t a, b; stream_next(st, &a, &b);
+    *z0 = zig_normal(a, st); *z1 = zig_normal(b, st);
+}
+/* the normals that n_pairs consecutive normal2() calls on the model stream (seed, particle, sweep) return */
+void orc_normal_stream(uint64_t seed, uint32_t particle, uint64_t sweep, int32_t n_pairs, double* out) {
+    stream_t st = { seed, particle, sweep, KIND_MODEL, 0 };
+    for (int32_t k = 0; k < n_pairs; ++k) normal2(&st, out + 2 * k, out + 2 * k + 1);
+}
+double orc_zig_normal(uint64_t seed, uint32_t particle, uint64_t sweep, uint32_t* block_io) {
+    stream_t st = { seed, particle, sweep, KIND_MODEL, *block_io };
+    uint64_t a, b; stream_next(&st, &a, &b);
+    double z = zig_normal(a, &st);
+    *block_io = st.block;
+    return z;
 }
 
 /* Poisson sampler (spec §3.3): one-uniform sequential-search inversion below 10, Hoermann's PTRS (1993) above,
@@ -604,8 +641,8 @@ static int model_sim(int32_t id, int32_t d, int32_t s, const double* mp, const d
     uint64_t a, b;
     switch (id) {
     case ORC_MODEL_GAUSS_MEAN: {        /* par: ybar_obs, sd_mean */
-        double z0, z1;
-        stream_next(&st, &a, &b); orc_normal_pair(a, b, &z0, &z1);
+        stream_next(&st, &a, &b);
+        double z0 = zig_normal(a, &st);
         double ysim = th[0] + mp[1] * z0;
         rho[0] = fabs(ysim - mp[0]);
         return 0; }
@@ -615,7 +652,7 @@ static int model_sim(int32_t id, int32_t d, int32_t s, const double* mp, const d
         double s1 = 0.0, s2 = 0.0;
         for (int k = 0; k < n; k += 2) {
             double z0, z1;
-            stream_next(&st, &a, &b); orc_normal_pair(a, b, &z0, &z1);
+            normal2(&st, &z0, &z1);
             double y = th[0] + sig * z0;
             s1 = s1 + y; s2 = s2 + y * y;
             if (k + 1 < n) { y = th[0] + sig * z1; s1 = s1 + y; s2 = s2 + y * y; }
@@ -628,7 +665,7 @@ static int model_sim(int32_t id, int32_t d, int32_t s, const double* mp, const d
         double x = mp[0];
         for (int t = 0; t < T; t += 2) {
             double z[2];
-            stream_next(&st, &a, &b); orc_normal_pair(a, b, &z[0], &z[1]);
+            normal2(&st, &z[0], &z[1]);
             for (int h = 0; h < 2 && t + h < T; ++h) {
                 double grow = (th[0] * x) * (1.0 - x / th[1]);
                 double noise = (th[2] * x) * z[h];
@@ -703,7 +740,8 @@ static void propose(int32_t proposal, const double* pp, int32_t d, const double*
         int64_t i1 = (int64_t)mulhi64(cb->A, (uint64_t)M);               /* :103-107: uniform pair i1 != i2 */
         int64_t i2 = (int64_t)mulhi64(cb->B, (uint64_t)(M - 1));
         if (i2 >= i1) i2++;
-        double g = pp[0] * (1.0 + pp[1] * normal32(cb->C));              /* :110 γ0*(1 + σ_γ*randn()) */
+        stream_t cs = { seed, particle, sweep, KIND_CTRL, 2 };           /* slow path of the jitter normal: control blocks 2, 3, ... */
+        double g = pp[0] * (1.0 + pp[1] * zig_normal(cb->C, &cs));       /* :110 γ0*(1 + σ_γ*randn()) */
         for (int32_t c = 0; c < d; ++c) out[c] = th[c] + g * (P[i1 * d + c] - P[i2 * d + c]);   /* :113 */
         *log_factor = 0.0;
     } else if (proposal == ORC_PROP_STRETCH) {
@@ -715,10 +753,7 @@ static void propose(int32_t proposal, const double* pp, int32_t d, const double*
     } else {
         stream_t st = { seed, particle, sweep, KIND_RW, 0 };
         double zs[16];
-        for (int32_t c = 0; c < d; c += 2) {
-            uint64_t a, b; stream_next(&st, &a, &b);
-            orc_normal_pair(a, b, &zs[c], &zs[c + 1]);
-        }
+        for (int32_t c = 0; c < d; c += 2) normal2(&st, &zs[c], &zs[c + 1]);
         if (d == 1) out[0] = th[0] + chol[0] * zs[0];                    /* :54 θ + rand(Normal(0, sqrt(Σ))) */
         else for (int32_t r = 0; r < d; ++r) {                           /* :42 θ .+ rand(MvNormal(0, Σ)) = θ + L z */
             double acc = 0.0;

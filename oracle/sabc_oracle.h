@@ -60,6 +60,9 @@ void   orc_sincos2pi(double u, double* s, double* c);
 double orc_logfact(double k);
 void   orc_normal_pair(uint64_t a, uint64_t b, double* z0, double* z1);
 int64_t orc_poisson(double lam, uint64_t seed, uint32_t particle, uint64_t sweep, uint32_t* block_io);
+/* one ziggurat normal from the next block(s) of the model stream (seed, particle, sweep); *block_io advances */
+void   orc_normal_stream(uint64_t seed, uint32_t particle, uint64_t sweep, int32_t n_pairs, double* out);
+double orc_zig_normal(uint64_t seed, uint32_t particle, uint64_t sweep, uint32_t* block_io);
 double orc_treesum(const double* x, int64_t n);
 
 int64_t orc_ecdf_build(const double* x, int64_t n, double* knots_out /* n+2 */);

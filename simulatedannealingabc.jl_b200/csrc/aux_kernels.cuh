@@ -28,9 +28,21 @@ static __global__ void k_ecdf_ends(double* knots, int64_t n_pos) {   // values =
     knots[0] = 0.0;
     knots[n_pos + 1] = knots[n_pos] * 1.5;
 }
-static __global__ void k_sample16(const double* in, int64_t cnt_out, double* out) {   // out has cnt_out + ECDF_PAD entries
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt_out + ECDF_PAD; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = i < cnt_out ? in[i * ECDF_FANOUT] : dinf();
+// one index level (plugin.cuh, "ECDF"): from the natural array `in` (cnt entries) the probe-ordered nodes of the blocks below
+// every 9th entry, and the next natural level (those 9th entries), padded with +inf up to next_len
+static __global__ void k_ecdf_level(const double* in, int64_t cnt, int64_t n_nodes, double* nodes, double* next, int64_t next_len) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < n_nodes * ECDF_NODE; i += stride) {
+        const int s = (int)(i & 7);
+        const int within = s == 0 ? 3 : s == 1 ? 6 : s == 2 ? 1 : s == 3 ? 2 : s == 4 ? 4 : s == 5 ? 5 : s == 6 ? 7 : 8;   // [e3 e6 | e1 e2 | e4 e5 | e7 e8]
+        const int64_t idx = (i >> 3) * ECDF_STRIDE + within;
+        nodes[i] = idx < cnt ? in[idx] : dinf();
+    }
+    for (int64_t i = t0; i < next_len; i += stride) next[i] = i < n_nodes ? in[i * ECDF_STRIDE] : dinf();
+}
+static __global__ void k_copy_pad_inf(const double* in, int64_t cnt, double* out, int64_t len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = i < cnt ? in[i] : dinf();
 }
 // compressed ECDF: K rank-uniform quantiles x[floor(i (m-1)/(K-1))], i = 0..K-1, of the m sorted positive distances
 static __global__ void k_ecdf_subsample(const double* sorted_pos, int64_t m, int K, double* out /* K + 2 + ECDF_PAD */) {

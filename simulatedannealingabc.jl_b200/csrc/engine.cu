@@ -5,8 +5,7 @@
 // in HBM, one population update is a fixed sequence of kernels whose control state (iteration
 // number, ε, accept counters, resampling trigger, history cursor) lives in device memory, so the
 // sequence is captured once in a CUDA graph and replayed without host round trips.
-#include "aux_kernels.cuh"
-#include "common.h"
+#include "ecdf_index.cuh"
 #include "nccl_dyn.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
@@ -150,28 +149,12 @@ static int free_ecdf(sabc_engine* e) {
 
 // Build the index levels of statistic j over knots already resident in `knots` (device, L entries).
 static int ecdf_attach(sabc_engine* e, int j, DevBuf<double>* knots, int64_t L, int top_max) {
-    EcdfStat& st = e->h_ecdf[j];
-    std::memset(&st, 0, sizeof st);
-    st.L = L; st.lev[0] = knots->p; st.cnt[0] = L; st.nlev = 1;
-    SABC_CUDA(cudaMemcpyAsync(&st.kmax, knots->p + (L - 1), sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    while (st.cnt[st.nlev - 1] > top_max) {
-        if (st.nlev >= ECDF_MAX_LEVELS) return set_error(SABC_ERR_INVALID, "ECDF table too large for %d index levels", ECDF_MAX_LEVELS);
-        const int64_t cnt = (st.cnt[st.nlev - 1] + ECDF_FANOUT - 1) / ECDF_FANOUT;
-        auto* b = new DevBuf<double>();
-        e->ecdf_bufs.push_back(b);
-        SABC_CUDA(b->alloc((size_t)cnt + ECDF_PAD));
-        const int grid = (int)std::min<int64_t>((cnt + ECDF_PAD + 255) / 256, 4096);
-        k_sample16<<<grid, 256, 0, e->stream>>>(st.lev[st.nlev - 1], cnt, b->p);
-        SABC_CUDA(cudaGetLastError());
-        st.lev[st.nlev] = b->p; st.cnt[st.nlev] = cnt; st.nlev++;
-    }
-    SABC_CUDA(cudaStreamSynchronize(e->stream));
-    return 0;
+    return ecdf_build_index(e->h_ecdf[j], knots->p, L, top_max, e->ecdf_bufs, e->stream);
 }
 
 static int ecdf_finalize(sabc_engine* e) {
     int off = 0;
-    for (int j = 0; j < e->S; ++j) { e->h_ecdf[j].top_off = off; off += (int)((e->h_ecdf[j].cnt[e->h_ecdf[j].nlev - 1] + 1) & ~(int64_t)1); }   // even: 16-byte bulk copies
+    for (int j = 0; j < e->S; ++j) { e->h_ecdf[j].top_off = off; off += e->h_ecdf[j].top_pow2; }
     e->top_doubles = off;
     SABC_CUDA(e->b_ecdf.ensure(MAX_S));
     SABC_CUDA(cudaMemcpyAsync(e->b_ecdf.p, e->h_ecdf, sizeof(EcdfStat) * e->S, cudaMemcpyHostToDevice, e->stream));
@@ -193,7 +176,7 @@ static int ecdf_finalize(sabc_engine* e) {
     return 0;
 }
 
-static int top_max_for(int S) { return std::max(64, std::min(2048, 6144 / S)); }
+static int top_max_for(int S) { return ecdf_top_max(S); }
 
 // build_cdf for column j from `d_col` (n values on the device)   src/cdf_estimators.jl:23-44
 static int ecdf_build_column(sabc_engine* e, int j, const double* d_col, int64_t n, DevBuf<double>& keys,
@@ -223,7 +206,7 @@ static int ecdf_build_column(sabc_engine* e, int j, const double* d_col, int64_t
         SABC_CUDA(cudaStreamSynchronize(e->stream));
         e->ecdf_bufs.pop_back(); delete knots;                                // the full sorted sample is not kept
         e->ecdf_bufs.push_back(small);
-        return ecdf_attach(e, j, small, (int64_t)K + 2, std::max(top_max_for(e->S), K + 2));
+        return ecdf_attach(e, j, small, (int64_t)K + 2, std::max(top_max_for(e->S), pow2_ceil(K + 2)));
     }
     k_ecdf_ends<<<1, 1, 0, e->stream>>>(knots->p, (int64_t)n_pos);
     SABC_CUDA(cudaGetLastError());
@@ -542,9 +525,9 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     if (n_local < 4) return set_error(SABC_ERR_INVALID, "need at least 4 particles per GPU (each half >= 2)");
     if (c->n_particles > 0xffffffffLL) return set_error(SABC_ERR_INVALID, "n_particles exceeds 2^32-1");
     if (c->resample <= 0) return set_error(SABC_ERR_INVALID, "resample must be positive");
-    if (c->ecdf_max_knots != 0 && (c->ecdf_max_knots < 2 || (int64_t)(c->ecdf_max_knots + 2) * c->n_stats * 8 > 200 * 1024))
-        return set_error(SABC_ERR_INVALID, "ecdf_max_knots must be 0 or in [2, %d] for %d statistics (the compressed tables live in shared memory)",
-                         (int)(200 * 1024 / 8 / c->n_stats - 2), c->n_stats);
+    if (c->ecdf_max_knots != 0 && (c->ecdf_max_knots < 2 || c->ecdf_max_knots > (1 << 20) || (int64_t)pow2_ceil(c->ecdf_max_knots + 2) * c->n_stats * 8 > 200 * 1024))
+        return set_error(SABC_ERR_INVALID, "ecdf_max_knots must be 0 or at least 2 with pow2(K + 2) * %d statistics * 8 bytes <= 200 KB (the compressed tables live in shared memory, "
+                         "padded to a power of two: K = 2^k - 2 wastes nothing)", c->n_stats);
 
     int ndev = 0;
     SABC_CUDA(cudaGetDeviceCount(&ndev));
@@ -996,12 +979,13 @@ int sabc_get_ecdf(sabc_engine* e, int32_t stat, double* knots_out, int64_t* L) {
     if (L) *L = e->h_ecdf[stat].L;
     if (knots_out) {
         SABC_CUDA(cudaSetDevice(e->device));
-        SABC_CUDA(cudaMemcpy(knots_out, e->h_ecdf[stat].lev[0], (size_t)e->h_ecdf[stat].L * sizeof(double), cudaMemcpyDeviceToHost));
+        SABC_CUDA(cudaMemcpy(knots_out, e->h_ecdf[stat].knots, (size_t)e->h_ecdf[stat].L * sizeof(double), cudaMemcpyDeviceToHost));
     }
     return 0;
 }
 int sabc_set_ecdf(sabc_engine* e, int32_t stat, const double* knots, int64_t L) {
     if (!e || stat < 0 || stat >= e->S || !knots || L < 3) return set_error(SABC_ERR_INVALID, "bad ECDF argument");
+    if (knots[0] != 0.0) return set_error(SABC_ERR_INVALID, "knots[0] must be 0 (values = [0; sort(x); ...], src/cdf_estimators.jl:33)");
     SABC_CUDA(cudaSetDevice(e->device));
     auto* b = new DevBuf<double>();
     e->ecdf_bufs.push_back(b);

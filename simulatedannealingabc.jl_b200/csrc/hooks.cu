@@ -1,8 +1,7 @@
 // hooks.cu -- parity hooks of the C ABI: each runs the ENGINE'S OWN device functions on
 // caller-supplied host arrays (copy in, one kernel, copy out), so tests can compare single steps
 // of the path bit-for-bit with the oracle.  No CPU computation happens here.
-#include "aux_kernels.cuh"
-#include "common.h"
+#include "ecdf_index.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cstring>
@@ -74,34 +73,6 @@ __global__ void k_ptrs_filter_check(const double* lam, int n_lam, int64_t attemp
     atomicMax(ratio_bits + 0, (unsigned long long)__double_as_longlong(r1));   // non-negative doubles order like integers
     atomicMax(ratio_bits + 1, (unsigned long long)__double_as_longlong(r2));
 }
-#if defined(SABC_EXPERIMENTAL_PTRS2)
-// experimental attempt (ptrs2_experimental.cuh) against the product attempt on `attempts` candidates:
-// counts = {attempts, undecided by the approximate candidate, acceptance tests reached, undecided by filter 2, wrong}
-__global__ void k_ptrs2_check(const double* lam, int n_lam, int64_t attempts, uint64_t seed, unsigned long long* counts) {
-    unsigned long long c[5] = {0, 0, 0, 0, 0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < attempts; i += (int64_t)gridDim.x * blockDim.x) {
-        const double l = lam[i % n_lam];
-        Stream st(seed, (uint32_t)i, (uint64_t)(i >> 32), KIND_MODEL);
-        const U64x2 w = st.draw();
-        double kf0, num = 0.0, den = 0.0, kf1;
-        int s0 = ptrs_candidate(l, w, kf0, num, den);
-        if (s0 == 2) s0 = (int)ptrs_exact(l, kf0, num, den);
-        float numf = 0.0f, denf = 0.0f;
-        int s1 = ptrs_candidate_mufu(l, w, kf1, numf, denf);
-        c[0]++;
-        if (s1 == 3) { c[1]++; continue; }
-        if (s1 == 2) {
-            c[2]++;
-            float T, E;
-            const int dec = ptrs_filter_mufu2(l, kf1, numf, denf, T, E);
-            if (dec == 0) { c[3]++; if (kf1 != kf0) c[4]++; continue; }
-            s1 = dec > 0;
-        }
-        if (s1 != s0 || (s0 == 1 && kf1 != kf0)) c[4]++;
-    }
-    for (int j = 0; j < 5; ++j) if (c[j]) atomicAdd(counts + j, c[j]);
-}
-#endif
 __global__ void k_accept(int64_t m, int s, const double* uo, const double* un, const double* eps, int n_eps, const double* dlp,
                          const double* lf, const double* U, uint8_t* acc) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
@@ -128,7 +99,7 @@ __global__ void k_propose(const double* act, int64_t n, const double* ina, int64
     const uint32_t pid = pbase + (uint32_t)i;
     const CtrlWords cw = ctrl_words(seed, pid, sweep);
     const InactiveGather<D> P{ina, M};
-    if (PROP == PROP_DE) propose_de<D>(th, P, M, p0, p1, cw, thp, lf);
+    if (PROP == PROP_DE) propose_de<D>(th, P, M, p0, p1, cw, Stream(seed, pid, sweep, KIND_CTRL), thp, lf);
     else if (PROP == PROP_STRETCH) propose_stretch<D>(th, P, M, p0, cw, thp, lf);
     else propose_rw<D>(th, chol, seed, pid, sweep, thp, lf);
     for (int c = 0; c < D; ++c) out[c * n + i] = thp[c];
@@ -154,18 +125,8 @@ struct HookEcdf {
     DevBuf<EcdfStat> d_st;
     ~HookEcdf() { for (auto* b : levels) delete b; }
     int attach(const double* d_knots, int64_t L, int top_max) {
-        st.L = L; st.lev[0] = d_knots; st.cnt[0] = L; st.nlev = 1; st.top_off = 0;
-        SABC_CUDA(cudaMemcpy(&st.kmax, d_knots + (L - 1), sizeof(double), cudaMemcpyDeviceToHost));
-        while (st.cnt[st.nlev - 1] > top_max) {
-            if (st.nlev >= ECDF_MAX_LEVELS) return set_error(SABC_ERR_INVALID, "ECDF table too large");
-            const int64_t cnt = (st.cnt[st.nlev - 1] + ECDF_FANOUT - 1) / ECDF_FANOUT;
-            auto* b = new DevBuf<double>();
-            levels.push_back(b);
-            SABC_CUDA(b->alloc((size_t)cnt + ECDF_PAD));
-            k_sample16<<<grid_for(cnt + ECDF_PAD), 256>>>(st.lev[st.nlev - 1], cnt, b->p);
-            SABC_CUDA(cudaGetLastError());
-            st.lev[st.nlev] = b->p; st.cnt[st.nlev] = cnt; st.nlev++;
-        }
+        SABC_TRY(ecdf_build_index(st, d_knots, L, top_max, levels, nullptr));
+        st.top_off = 0;
         SABC_CUDA(d_st.alloc(1));
         SABC_CUDA(cudaMemcpy(d_st.p, &st, sizeof st, cudaMemcpyHostToDevice));
         return 0;
@@ -217,20 +178,6 @@ int sabc_ptrs_filter_check(const double* lam, int32_t n_lam, int64_t attempts, u
     return 0;
 }
 
-#if defined(SABC_EXPERIMENTAL_PTRS2)
-int sabc_ptrs2_check(const double* lam, int32_t n_lam, int64_t attempts, uint64_t seed, int64_t counts_out[5]) {
-    if (!lam || n_lam < 1 || attempts < 0 || !counts_out) return set_error(SABC_ERR_INVALID, "bad argument");
-    DevBuf<double> dl; DevBuf<unsigned long long> dc;
-    SABC_TRY(upload(dl, lam, (size_t)n_lam)); SABC_CUDA(dc.alloc(5));
-    SABC_CUDA(cudaMemset(dc.p, 0, 5 * sizeof(unsigned long long)));
-    k_ptrs2_check<<<148 * 8, 256>>>(dl.p, n_lam, attempts, seed, dc.p);
-    SABC_CUDA(cudaGetLastError());
-    unsigned long long h[5];
-    SABC_TRY(download(h, dc, 5));
-    for (int j = 0; j < 5; ++j) counts_out[j] = (int64_t)h[j];
-    return 0;
-}
-#endif
 
 // build_cdf(::AbstractVector)  src/cdf_estimators.jl:23-44
 int sabc_ecdf_build(const double* dist, int64_t n, double* knots_out, int64_t* L) {
@@ -257,6 +204,7 @@ int sabc_ecdf_build(const double* dist, int64_t n, double* knots_out, int64_t* L
 // cdfs_dist_prior(rho)  src/cdf_estimators.jl:68-70, through the same staged multi-level index as the engine
 int sabc_ecdf_transform(const double* knots, int64_t L, const double* rho, int64_t m, double* u_out) {
     if (!knots || !rho || !u_out || L < 3) return set_error(SABC_ERR_INVALID, "bad argument");
+    if (knots[0] != 0.0) return set_error(SABC_ERR_INVALID, "knots[0] must be 0 (values = [0; sort(x); ...], src/cdf_estimators.jl:33)");
     DevBuf<double> dk, dr, du;
     SABC_CUDA(dk.alloc((size_t)L + ECDF_PAD));
     SABC_CUDA(cudaMemcpy(dk.p, knots, (size_t)L * sizeof(double), cudaMemcpyHostToDevice));
@@ -264,7 +212,7 @@ int sabc_ecdf_transform(const double* knots, int64_t L, const double* rho, int64
     SABC_TRY(upload(dr, rho, (size_t)m)); SABC_CUDA(du.alloc((size_t)m));
     HookEcdf h;
     SABC_TRY(h.attach(dk.p, L, 2048));
-    const size_t smem = (size_t)((h.st.cnt[h.st.nlev - 1] + 1) & ~(int64_t)1) * sizeof(double);
+    const size_t smem = (size_t)h.st.top_pow2 * sizeof(double);
     k_transform1<<<grid_for(m), CHUNK, smem>>>(dr.p, m, h.d_st.p, du.p);
     SABC_CUDA(cudaGetLastError());
     return download(u_out, du, (size_t)m);

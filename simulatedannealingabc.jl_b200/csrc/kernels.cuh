@@ -160,16 +160,6 @@ struct PopView {                 // structure-of-arrays particle state of one GP
     int64_t ld;
 };
 
-// -DSABC_EXPERIMENTAL_RK_ALL (NOT in the product build, never run on a GPU): the fused and the propose kernels also take the
-// Philox round keys from the parameter block, as the simulation kernel of the split path does
-#if defined(SABC_EXPERIMENTAL_RK_ALL)
-#define SABC_RK_ALL(a) ((a).rk.k)
-#define SABC_GRID_CONSTANT __grid_constant__
-#else
-#define SABC_RK_ALL(a) nullptr
-#define SABC_GRID_CONSTANT
-#endif
-
 struct UpdateArgs {
     PopView pop;
     int64_t act_off, act_n, ina_off, ina_n;   // active / inactive half (local indices)
@@ -219,6 +209,10 @@ struct InitArgs {
     ModelPar mp;
 };
 
+// a model that never draws normals declares `static constexpr int NO_NORMALS = 1` and its simulation kernel skips the table
+template <class M, class = void> struct model_draws_normals { static constexpr bool value = true; };
+template <class M> struct model_draws_normals<M, decltype((void)M::NO_NORMALS)> { static constexpr bool value = false; };
+
 template <int D>
 struct InactiveGather {
     const double* base; int64_t ld;
@@ -227,15 +221,13 @@ struct InactiveGather {
 
 // Stage the top index level of every statistic in shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP): one
 // elected thread posts the expected byte count on an mbarrier and issues one bulk copy per statistic; every thread then
-// waits on the barrier's phase.  Sizes are rounded up to 16 bytes (levels carry +inf padding, offsets are even).
+// waits on the barrier's phase.  The staged levels are padded to a power of two >= 2 entries: sizes are multiples of 16 bytes.
 SABC_D void stage_ecdf_top(const EcdfStat* ecdf, int S, double* s_top) {
 #if defined(SABC_NO_TMA)
     for (int j = 0; j < S; ++j) {
         const EcdfStat& e = ecdf[j];
-        const int top = e.nlev - 1;
-        const double* src = e.lev[top];
         double* dst = s_top + e.top_off;
-        for (int64_t i = threadIdx.x; i < e.cnt[top]; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < e.top_pow2; i += blockDim.x) dst[i] = e.top[i];
     }
     __syncthreads();
 #else
@@ -248,15 +240,14 @@ SABC_D void stage_ecdf_top(const EcdfStat* ecdf, int S, double* s_top) {
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t total = 0;
-        for (int j = 0; j < S; ++j) total += (uint32_t)(((ecdf[j].cnt[ecdf[j].nlev - 1] + 1) & ~(int64_t)1) * 8);
+        for (int j = 0; j < S; ++j) total += (uint32_t)ecdf[j].top_pow2 * 8u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total) : "memory");
         for (int j = 0; j < S; ++j) {
             const EcdfStat& e = ecdf[j];
-            const int top = e.nlev - 1;
-            const uint32_t bytes = (uint32_t)(((e.cnt[top] + 1) & ~(int64_t)1) * 8);
+            const uint32_t bytes = (uint32_t)e.top_pow2 * 8u;
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_top + e.top_off);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(e.lev[top]), "r"(bytes), "r"(mbar) : "memory");
+                         ::"r"(dst), "l"(e.top), "r"(bytes), "r"(mbar) : "memory");
         }
     }
     uint32_t done = 0;
@@ -272,17 +263,20 @@ SABC_D void stage_ecdf_top(const EcdfStat* ecdf, int S, double* s_top) {
 // the partial reductions the ε update, the resampling weights and the history need.
 // ------------------------------------------------------------------------------------------------
 template <class M, int PROP>
-__global__ void __launch_bounds__(CHUNK) update_half_kernel(const SABC_GRID_CONSTANT UpdateArgs a) {
+__global__ void __launch_bounds__(CHUNK, M::FUSED_MIN_BLOCKS) update_half_kernel(const UpdateArgs a) {
     constexpr int D = M::D, S = M::S;
     extern __shared__ __align__(128) double s_top[];
     __shared__ unsigned long long s_acc[2 * S + 1];
     __shared__ double s_w[S][8];
     __shared__ double s_chol[PROP == PROP_RW ? D * D : 1];
+    __shared__ ZigEntry s_zig[256];
 
     const int tid = threadIdx.x;
     for (int k = tid; k < 2 * S + 1; k += CHUNK) s_acc[k] = 0ull;
     if (PROP == PROP_RW) for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k];
+    const uint32_t zig = stage_zig(s_zig);
     stage_ecdf_top(a.ecdf, S, s_top);
+    __syncthreads();
 
     const uint64_t sweep = 2ull * (uint64_t)a.ds->t + (uint64_t)a.half;
     double eps[S];
@@ -304,13 +298,13 @@ __global__ void __launch_bounds__(CHUNK) update_half_kernel(const SABC_GRID_CONS
             double th[D], thp[D], lf;
 #pragma unroll
             for (int c = 0; c < D; ++c) th[c] = a.pop.theta[c * ld + gi];
-            const CtrlWords cw = ctrl_words(a.seed, pid, sweep, SABC_RK_ALL(a));
-            if (PROP == PROP_DE) propose_de<D>(th, P, a.ina_n, a.prop0, a.prop1, cw, thp, lf);
+            const CtrlWords cw = ctrl_words(a.seed, pid, sweep);
+            if (PROP == PROP_DE) propose_de<D>(th, P, a.ina_n, a.prop0, a.prop1, cw, Stream(a.seed, pid, sweep, KIND_CTRL, nullptr, zig), thp, lf);
             else if (PROP == PROP_STRETCH) propose_stretch<D>(th, P, a.ina_n, a.prop0, cw, thp, lf);
-            else propose_rw<D>(th, s_chol, a.seed, pid, sweep, thp, lf);
+            else propose_rw<D>(th, s_chol, a.seed, pid, sweep, thp, lf, zig);
             const double lpp = prior_logpdf<D>(a.prior, thp);
             if (lpp > -dinf()) {                                       // :314 (no simulation outside the support)
-                Stream st(a.seed, pid, sweep, KIND_MODEL, SABC_RK_ALL(a));
+                Stream st(a.seed, pid, sweep, KIND_MODEL, nullptr, zig);
                 M::sim(thp, a.mp, st, rp);                              // :315
                 double Ssum = 0.0;
 #pragma unroll
@@ -367,11 +361,14 @@ __global__ void __launch_bounds__(CHUNK) update_half_kernel(const SABC_GRID_CONS
 // Results are identical to the fused kernel: every particle uses the same Philox streams and arithmetic.
 // ------------------------------------------------------------------------------------------------
 template <class M, int PROP>
-__global__ void __launch_bounds__(CHUNK) propose_kernel(const SABC_GRID_CONSTANT UpdateArgs a, const SplitScratch w) {
+__global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, const SplitScratch w) {
     constexpr int D = M::D;
     __shared__ double s_chol[PROP == PROP_RW ? D * D : 1];
+    __shared__ ZigEntry s_zig[PROP == PROP_STRETCH ? 1 : 256];
     const int tid = threadIdx.x, lane = tid & 31;
-    if (PROP == PROP_RW) { for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k]; __syncthreads(); }
+    if (PROP == PROP_RW) for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k];
+    const uint32_t zig = PROP == PROP_STRETCH ? 0u : stage_zig(s_zig);
+    __syncthreads();
     const uint64_t sweep = 2ull * (uint64_t)a.ds->t + (uint64_t)a.half;
     const int64_t ld = a.pop.ld;
     const int64_t n_groups = (a.act_n + CHUNK - 1) / CHUNK;
@@ -386,10 +383,10 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const SABC_GRID_CONSTANT
             double th[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) th[c] = a.pop.theta[c * ld + gi];
-            const CtrlWords cw = ctrl_words(a.seed, pid, sweep, SABC_RK_ALL(a));
-            if (PROP == PROP_DE) propose_de<D>(th, P, a.ina_n, a.prop0, a.prop1, cw, thp, lf);
+            const CtrlWords cw = ctrl_words(a.seed, pid, sweep);
+            if (PROP == PROP_DE) propose_de<D>(th, P, a.ina_n, a.prop0, a.prop1, cw, Stream(a.seed, pid, sweep, KIND_CTRL, nullptr, zig), thp, lf);
             else if (PROP == PROP_STRETCH) propose_stretch<D>(th, P, a.ina_n, a.prop0, cw, thp, lf);
-            else propose_rw<D>(th, s_chol, a.seed, pid, sweep, thp, lf);
+            else propose_rw<D>(th, s_chol, a.seed, pid, sweep, thp, lf, zig);
             lpp = prior_logpdf<D>(a.prior, thp);
             ok = lpp > -dinf();                                         // :314
         }
@@ -417,7 +414,10 @@ template <class M>
 __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kernel(const __grid_constant__ UpdateArgs a, const SplitScratch w) {
     constexpr int D = M::D, S = M::S;
     extern __shared__ __align__(128) double s_top[];
+    __shared__ ZigEntry s_zig[model_draws_normals<M>::value ? 256 : 1];
+    const uint32_t zig = model_draws_normals<M>::value ? stage_zig(s_zig) : 0u;
     stage_ecdf_top(a.ecdf, S, s_top);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint64_t sweep = 2ull * (uint64_t)a.ds->t + (uint64_t)a.half;
     double eps[S];
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
             double thp[D], rp[S], up[S];
 #pragma unroll
             for (int c = 0; c < D; ++c) thp[c] = w.theta[c * w.cap + q];
-            Stream st(a.seed, pid, sweep, KIND_MODEL, a.rk.k);
+            Stream st(a.seed, pid, sweep, KIND_MODEL, a.rk.k, zig);
             st.warp_mask = live;
             M::sim(thp, a.mp, st, rp);                                  // :315
             double Ssum = 0.0;

@@ -70,10 +70,11 @@ SABC_HD U64x2 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c
 struct Stream {
     uint32_t k0, k1, particle, sweep_lo, tag, next;
     uint32_t warp_mask;   // lanes known to call the model together (0: the model asks __activemask())
+    uint32_t zig_smem;    // shared-space address of a CTA-staged copy of the ziggurat table (stage_zig), 0: read it through L1
     const uint32_t* rk;   // optional precomputed round keys of the same seed (RoundKeys::k), else nullptr
-    SABC_HD Stream(uint64_t seed, uint32_t particle_, uint64_t sweep, uint32_t kind, const uint32_t* rk_ = nullptr)
+    SABC_HD Stream(uint64_t seed, uint32_t particle_, uint64_t sweep, uint32_t kind, const uint32_t* rk_ = nullptr, uint32_t zig_smem_ = 0)
         : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), particle(particle_), sweep_lo((uint32_t)sweep),
-          tag(kind | ((uint32_t)(sweep >> 32) << 4)), next(0), warp_mask(0), rk(rk_) {}
+          tag(kind | ((uint32_t)(sweep >> 32) << 4)), next(0), warp_mask(0), zig_smem(zig_smem_), rk(rk_) {}
     SABC_HD U64x2 block(uint32_t j) const {
         return rk ? philox4x32_10_rk(particle, sweep_lo, j, tag, rk) : philox4x32_10(particle, sweep_lo, j, tag, k0, k1);
     }
@@ -84,18 +85,121 @@ SABC_HD double u53(uint64_t x) { return (double)(x >> 11) * 0x1p-53; }          
 SABC_HD double u53_open0(uint64_t x) { return (double)((x >> 11) + 1) * 0x1p-53; }  // (0,1]
 SABC_HD double u53_mid(uint64_t x) { return ((double)(x >> 11) + 0.5) * 0x1p-53; }   // (0,1), for quantile transforms
 
-// Box-Muller pair from one block; stands in for randn()
+// Box-Muller pair from one block: the normal behind the PRIOR draws (initialization only; addressed by explicit block numbers)
 SABC_HD void normal_pair(const U64x2 w, double& z0, double& z1) {
     const double r = sqrt(-2.0 * det_log(u53_open0(w.a)));
     double sn, cs;
     det_sincos2pi(u53(w.b), sn, cs);
     z0 = r * cs; z1 = r * sn;
 }
-// one normal from a single 64-bit word (two 32-bit uniforms) -- the DE gamma jitter
-SABC_HD double normal32(uint64_t c) {
-    const double u1 = (double)((c & 0xffffffffULL) + 1) * 0x1p-32;
-    const double u2 = (double)(c >> 32) * 0x1p-32;
-    return sqrt(-2.0 * det_log(u1)) * det_cos2pi(u2);
+
+// ------------------------------------------------------------------------------------------------
+// randn() on the hot path (proposals.jl:110 DE jitter, :42,54 RandomWalk, the models' noise): 256-layer ziggurat
+// (Marsaglia & Tsang 2000; Julia's own randn() is a ziggurat too) on ONE 64-bit Philox word:
+//   bits 0..7 layer i, bit 8 sign, bits 11..63 the 53-bit integer m;  x = m * ZIG_W[i]  (one exact conversion, one rounded product)
+//   m < ZIG_K[i]  (98.5 %)  ->  +-x.   Otherwise the slow path takes one extra block e of the SAME stream:
+//   i == 0: tail beyond R: xx = -log(U(e.a)) / R, yy = -log(U(e.b)), accept R + xx when 2 yy > xx^2, else next block, ...
+//   i >= 1: wedge: accept x when ZIG_F[i] + U(e.a) (ZIG_F[i+1] - ZIG_F[i]) < exp(-x^2/2), else start again with the word e.b.
+// Tables: tools/gen_ziggurat.py -> csrc/zig_tables.cuh.  A stream's blocks are consumed in order,
+// so the result is a pure function of (seed, particle, sweep, kind) like every other draw.
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) ZigEntry { unsigned long long k; double w; };
+#if defined(__CUDACC__)
+namespace zig_dev {
+#define ZIG_TABLE_QUALIFIER static __device__ const
+#include "zig_tables.cuh"
+#undef ZIG_TABLE_QUALIFIER
+}
+#endif
+namespace zig_host {
+#define ZIG_TABLE_QUALIFIER static const
+#include "zig_tables.cuh"
+#undef ZIG_TABLE_QUALIFIER
+}
+#if defined(__CUDA_ARCH__)
+#define SABC_ZIG_F(i) __ldg(&zig_dev::ZIG_F[i])
+#else
+#define SABC_ZIG_F(i) zig_host::ZIG_F[i]
+#endif
+
+struct ZigSlow { double z; uint32_t next; };
+// the 1.5 % that miss the fast test, every argument by value so that the caller's Stream stays in registers
+SABC_HD ZigSlow zig_slow(uint64_t w, uint32_t k0, uint32_t k1, uint32_t particle, uint32_t sweep_lo, uint32_t tag, uint32_t next) {
+    for (;;) {
+        const uint32_t idx = (uint32_t)w & 255u;
+        const uint64_t m = w >> 11;
+        const uint64_t sign = (w & 256u) << 55;
+#if defined(__CUDA_ARCH__)
+        const unsigned long long kk = zig_dev::ZIG_KW[idx].k; const double ww = zig_dev::ZIG_KW[idx].w;
+#else
+        const unsigned long long kk = zig_host::ZIG_KW[idx].k; const double ww = zig_host::ZIG_KW[idx].w;
+#endif
+        const double x = (double)m * ww;
+        if (m < kk) return ZigSlow{bits_f64(f64_bits(x) | sign), next};
+        U64x2 e = philox4x32_10(particle, sweep_lo, next++, tag, k0, k1);
+        if (idx == 0) {
+            for (;;) {
+                const double xx = (-det_log(u53_open0(e.a))) * ZIG_INV_R;
+                const double yy = -det_log(u53_open0(e.b));
+                if (yy + yy > xx * xx) return ZigSlow{bits_f64(f64_bits(ZIG_R + xx) | sign), next};
+                e = philox4x32_10(particle, sweep_lo, next++, tag, k0, k1);
+            }
+        }
+        const double f0 = SABC_ZIG_F(idx), f1 = SABC_ZIG_F(idx + 1);
+        const double y = f0 + u53(e.a) * (f1 - f0);
+        if (y < det_exp((-0.5 * x) * x)) return ZigSlow{bits_f64(f64_bits(x) | sign), next};
+        w = e.b;
+    }
+}
+// out-of-line form for models with many call sites (an ABI call saves the live registers to local memory: measured on the fused
+// Gaussian kernel as 800 MB of extra L2 traffic per half-sweep, so the default is the inline form)
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+ZigSlow zig_slow_call(uint64_t w, uint32_t k0, uint32_t k1, uint32_t particle, uint32_t sweep_lo, uint32_t tag, uint32_t next) {
+    return zig_slow(w, k0, k1, particle, sweep_lo, tag, next);
+}
+// one normal from the word w; the slow path continues on st
+template <bool INLINE_SLOW = true>
+SABC_HD double zig_normal(uint64_t w, Stream& st) {
+    const uint32_t idx = (uint32_t)w & 255u;
+    const uint64_t m = w >> 11;
+#if defined(__CUDA_ARCH__)
+    // the layer is random per lane: from a shared-memory copy a warp's 32 lookups cost a few bank conflicts, through L1 up to 32 tag
+    // wavefronts -- the fused Gaussian kernels are bound by exactly those (profiles/), so their CTAs stage the 4 KB table
+    ulonglong2 e;
+    if (st.zig_smem) asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(e.x), "=l"(e.y) : "r"(st.zig_smem + idx * 16u));
+    else e = __ldg(reinterpret_cast<const ulonglong2*>(&zig_dev::ZIG_KW[idx]));
+    const unsigned long long kk = e.x; const double ww = __longlong_as_double((long long)e.y);
+#else
+    const unsigned long long kk = zig_host::ZIG_KW[idx].k; const double ww = zig_host::ZIG_KW[idx].w;
+#endif
+    const double x = (double)m * ww;
+    if (m < kk) return bits_f64(f64_bits(x) | ((w & 256u) << 55));
+    const ZigSlow s = INLINE_SLOW ? zig_slow(w, st.k0, st.k1, st.particle, st.sweep_lo, st.tag, st.next)
+                                  : zig_slow_call(w, st.k0, st.k1, st.particle, st.sweep_lo, st.tag, st.next);
+    st.next = s.next;
+    return s.z;
+}
+#if defined(__CUDACC__)
+// copy the layer table into the CTA's shared memory (all threads of the CTA; the caller synchronises before the first draw)
+SABC_D uint32_t stage_zig(ZigEntry* s_zig) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_zig[i] = zig_dev::ZIG_KW[i];
+    return (uint32_t)__cvta_generic_to_shared(s_zig);
+}
+#endif
+// two normals from the next block of st (stands in for two randn() calls)
+template <bool INLINE_SLOW = true>
+SABC_HD void normal2(Stream& st, double& z0, double& z1) {
+    const U64x2 w = st.draw();
+    z0 = zig_normal<INLINE_SLOW>(w.a, st);
+    z1 = zig_normal<INLINE_SLOW>(w.b, st);
+}
+SABC_HD double normal1(Stream& st) {
+    const U64x2 w = st.draw();
+    return zig_normal(w.a, st);
 }
 
 // correctly rounded reciprocal: 1.0/x on the host, the cheaper MUFU-seeded __drcp_rn on the device (same bits)
@@ -246,12 +350,6 @@ SABC_HD bool ptrs_exact(double lam, double kf, double num, double den) {
     return lhs <= rhs;
 }
 
-#if defined(SABC_EXPERIMENTAL_PTRS2) && defined(__CUDACC__)
-}  // namespace sabc
-#include "ptrs2_experimental.cuh"   // not in the product build: see the header of that file
-namespace sabc {
-#endif
-
 // Poisson(lam): one-uniform sequential-search inversion below 10, PTRS above, with the acceptance tests
 // rearranged to one reciprocal and one logarithm of a quotient.  One ATTEMPT consumes one Philox block (none when
 // lam <= 0) and either returns a count or rejects; this is the unit the SIR kernel interleaves across lanes so that a
@@ -274,12 +372,6 @@ SABC_HD bool poisson_attempt_d(double lam, Stream& st, double& k_out) {
         return true;
     }
     double kf, num = 0.0, den = 0.0;
-#if defined(SABC_EXPERIMENTAL_PTRS2) && defined(__CUDA_ARCH__)
-    {
-        const int s2 = ptrs_attempt2(lam, w, kf);
-        if (s2 != 3) { if (s2 == 1) k_out = kf; return s2 == 1; }
-    }
-#endif
     int s = ptrs_candidate(lam, w, kf, num, den);
     if (s == 2) {
 #if !defined(SABC_NO_PTRS_FILTER)

@@ -15,9 +15,8 @@ namespace sabc {
 constexpr int MAX_D = 8;            // max parameters per particle
 constexpr int MAX_S = 32;           // max summary statistics
 constexpr int MAX_MODEL_PAR = 40;   // doubles in a model parameter blob
-constexpr int ECDF_MAX_LEVELS = 8;
-constexpr int ECDF_FANOUT = 16;     // one 128-byte line of knots per index node
-constexpr int ECDF_PAD = 16;        // +inf entries appended to every level (whole-node loads never leave the buffer)
+constexpr int ECDF_MAX_LEVELS = 10;
+constexpr int ECDF_PAD = 16;        // +inf entries appended to a knot table
 constexpr int CHUNK = 256;          // particles per tree-sum group == threads per CTA
 
 enum Algorithm : int32_t { ALG_SINGLE_EPS = 0, ALG_MULTI_EPS = 1 };
@@ -189,13 +188,15 @@ SABC_HD CtrlWords ctrl_words(uint64_t seed, uint32_t particle, uint64_t sweep, c
     return CtrlWords{b0.a, b0.b, b1.a, b1.b};
 }
 
+// `ctrl` = the particle's control stream; the jitter normal comes from word C, its rare slow path from blocks 2, 3, ...
 template <int D, class Gather>
 SABC_HD void propose_de(const double (&th)[D], const Gather& P, int64_t M, double gamma0, double sigma_gamma,
-                        const CtrlWords& cw, double (&out)[D], double& log_factor) {
+                        const CtrlWords& cw, Stream ctrl, double (&out)[D], double& log_factor) {
     int64_t i1 = (int64_t)mulhi64(cw.A, (uint64_t)M);               // proposals.jl:103-107
     int64_t i2 = (int64_t)mulhi64(cw.B, (uint64_t)(M - 1));
     if (i2 >= i1) i2++;
-    const double g = gamma0 * (1.0 + sigma_gamma * normal32(cw.C)); // :110
+    ctrl.next = 2;
+    const double g = gamma0 * (1.0 + sigma_gamma * zig_normal(cw.C, ctrl)); // :110
 #pragma unroll
     for (int c = 0; c < D; ++c) out[c] = th[c] + g * (P(c, i1) - P(c, i2));   // :113
     log_factor = 0.0;
@@ -215,11 +216,11 @@ SABC_HD void propose_stretch(const double (&th)[D], const Gather& P, int64_t M, 
 // chol: row-major lower Cholesky factor of Σ (D>1) or sqrt(Σ) (D==1)   proposals.jl:42,54
 template <int D>
 SABC_HD void propose_rw(const double (&th)[D], const double* chol, uint64_t seed, uint32_t particle, uint64_t sweep,
-                        double (&out)[D], double& log_factor) {
-    Stream st(seed, particle, sweep, KIND_RW);
+                        double (&out)[D], double& log_factor, uint32_t zig_smem = 0) {
+    Stream st(seed, particle, sweep, KIND_RW, nullptr, zig_smem);
     double z[D + 1];
 #pragma unroll
-    for (int c = 0; c < D; c += 2) normal_pair(st.draw(), z[c], z[c + 1 < D ? c + 1 : D]);
+    for (int c = 0; c < D; c += 2) normal2(st, z[c], z[c + 1 < D ? c + 1 : D]);
     if (D == 1) {
         out[0] = th[0] + chol[0] * z[0];
     } else {
@@ -235,18 +236,31 @@ SABC_HD void propose_rw(const double (&th)[D], const double* chol, uint64_t seed
 }
 
 // ------------------------------------------------------------------------------------------------
-// ECDF: sorted knots K[0..L) in HBM plus a 16-ary sampled index (level k+1 = every 16th entry of
-// level k); the top level is staged in shared memory.  Evaluation follows Interpolations.jl's
-// LinearMonotonicInterpolation + Flat() exactly: bracket by
+// ECDF: sorted knots K[0..L) in HBM (level 0) plus a sampled index: level k+1 = every 9th entry of level k, until a level has
+// at most 2048 / 1024 / ... entries (power of two, by the number of statistics); that top level is staged in shared memory.
+// Evaluation follows Interpolations.jl's LinearMonotonicInterpolation + Flat() exactly: bracket by
 // searchsortedfirst-1, slope by division, one rounded multiply then one rounded add.
+//
+// What bounds the lookup on a B200 (profiles/r2_c5_*): every lane of a warp searches a different region, so every load
+// instruction costs one L1 wavefront PER LANE whatever its width up to 16 bytes, and the fused Gaussian kernels spend their time
+// on exactly those wavefronts (78 % of the L1 data-pipe peak with a 16-ary index searched by scalar probes: 20 loads per lookup).
+// The index is therefore laid out for two 16-byte probes per level: below entry m of level k+1 sit the eight entries
+// e1..e8 = A_k[9m+1 .. 9m+8], stored as one 64-byte node in PROBE ORDER [e3 e6 | e1 e2 | e4 e5 | e7 e8]; the first probe
+// (e3, e6) selects the pair of the second, and 3 c1 + c2 is the count of entries below x.  Every probed value also tightens
+// a running bracket (largest value < x, smallest value >= x), which by induction over the levels ends as (K[j], K[j+1]):
+// the knots themselves are never read again.  8 wavefronts per lookup at L = 10^7 instead of 20, a third of the instructions.
 // ------------------------------------------------------------------------------------------------
+constexpr int ECDF_NODE = 8;        // entries per node (64 bytes)
+constexpr int ECDF_STRIDE = 9;      // level k+1 samples every 9th entry of level k
 struct EcdfStat {
-    const double* lev[ECDF_MAX_LEVELS];   // lev[0] = knots
-    int64_t cnt[ECDF_MAX_LEVELS];
+    const double* knots;                      // K[0..L), natural order (returned by sabc_get_ecdf; not read by the lookup)
+    const double* node[ECDF_MAX_LEVELS];      // node[k]: probe-ordered nodes for the search inside level k, k = 0 .. nlev-2
+    const double* top;                        // top level, natural order, top_pow2 entries (+inf padded)
     int64_t L;
-    double kmax;                          // K[L-1]
-    int32_t nlev;                         // levels incl. knots; lev[nlev-1] is the staged one
-    int32_t top_off;                      // offset (doubles) of the staged level in shared memory
+    double kmax;                              // K[L-1]
+    int32_t nlev;                             // levels incl. the knots; level nlev-1 is the staged one
+    int32_t top_cnt, top_pow2;                // real / padded (power of two) entries of the top level
+    int32_t top_off;                          // offset (doubles) of the staged level in shared memory
 };
 
 // number of entries of sorted a[0..n) that are < x
@@ -260,74 +274,36 @@ SABC_HD int64_t count_less(const double* a, int64_t n, double x) {
 }
 
 #if defined(__CUDACC__)
-// the Metropolis test log(U) < L  (src/SimulatedAnnealingABC.jl:324).  -DSABC_EXPERIMENTAL_ACCEPT_FILTER (NOT in the product
-// build, never run on a GPU, see DEVELOPMENT.md) decides it with one MUFU.LG2 when |log U - L| exceeds the error of that
-// estimate (float(U): 6e-8, lg2.approx: 2 ulp of |log2 U| <= 60 -> 1e-5, one product: 3e-6; bound used 4e-5) and evaluates
-// det_log only for the ~1e-4 of the particles inside the band, so the decision -- and the trajectory -- is unchanged.
-SABC_D bool log_u_less(double U, double L) {
-#if defined(SABC_EXPERIMENTAL_ACCEPT_FILTER)
-    if (U > 0x1p-60) {
-        const double l = (double)__fmul_rn(0.693147180559945f, mufu_lg2(__double2float_rn(U)));
-        if (l < L - 4e-5) return true;
-        if (l > L + 4e-5) return false;
-    }
-#endif
-    return det_log(U) < L;
-}
-
-// same count over an array staged in shared memory, 8-ary: each round reads 7 pivots at once, so a 2048-entry level
-// costs 4 dependent shared-memory latencies instead of 11
-SABC_D int count_less_smem(const double* a, int n, double x) {
-    int lo = 0, len = n;
-    while (len > 0) {
-        const int step = (len + 7) >> 3;
-        int m = 0;
-#pragma unroll
-        for (int i = 1; i <= 7; ++i) {
-            const int q = i * step - 1;
-            m += (q < len && a[lo + q] < x) ? 1 : 0;       // pivots are sorted: the true ones form a prefix
-        }
-        lo += m * step;
-        len = (m == 7) ? len - 7 * step : (step - 1 < len - m * step ? step - 1 : len - m * step);
-    }
-    return lo;
-}
-// one 16-entry index node (an aligned 128-byte line, levels are padded with +inf): branch-free binary search, 5 probes.
-// Fetching the whole line at once (8 x 16 B, one latency) was measured 1.7x SLOWER on C5: the kernel is bound by
-// L1/LSU wavefronts of scattered accesses (63 % of peak, profiles/r1_c5_update_half_v0_ncu.txt), not by the probe chain.
-SABC_D int count_less16(const double* node, double x) {
-#if defined(SABC_EXPERIMENTAL_NODE2)
-    // NOT in the product build, never run on a GPU: the same count in two dependent rounds instead of five -- the quarter
-    // from entries 3, 7, 11, then the four entries of that quarter (sorted: the entries below x form a prefix).  Seven loads
-    // of one 128-byte line instead of five; the long-scoreboard stall of the Gaussian kernels sits on this chain.
-    const int qd = ((__ldg(node + 3) < x) ? 1 : 0) + ((__ldg(node + 7) < x) ? 1 : 0) + ((__ldg(node + 11) < x) ? 1 : 0);
-    const double* qn = node + 4 * qd;
-    return 4 * qd + ((__ldg(qn) < x) ? 1 : 0) + ((__ldg(qn + 1) < x) ? 1 : 0) + ((__ldg(qn + 2) < x) ? 1 : 0) + ((__ldg(qn + 3) < x) ? 1 : 0);
-#endif
-    int lo = 0;
-#pragma unroll
-    for (int step = 8; step >= 1; step >>= 1) lo += (__ldg(node + lo + step - 1) < x) ? step : 0;
-    return lo + ((__ldg(node + lo) < x) ? 1 : 0);
-}
+// the Metropolis test log(U) < L  (src/SimulatedAnnealingABC.jl:324)
+SABC_D bool log_u_less(double U, double L) { return det_log(U) < L; }
 
 SABC_D double ecdf_eval(const EcdfStat& e, const double* s_top, double rho) {
     const double x = rho > e.kmax ? e.kmax : (rho < 0.0 ? 0.0 : rho);        // Flat(): clamp to [K_1, K_L]
-    const int top = e.nlev - 1;
-    int64_t lb = count_less_smem(s_top + e.top_off, (int)e.cnt[top], x);    // searchsortedfirst on the top level
-    for (int lv = top - 1; lv >= 0; --lv) {
-        if (lb > 0) {
-            const int64_t base = (lb - 1) * ECDF_FANOUT;
-            lb = base + (int64_t)count_less16(e.lev[lv] + base, x);
-        }
+    // searchsortedfirst on the staged top level: branch-free bisection over a power-of-two table padded with +inf
+    const double* T = s_top + e.top_off;
+    int c = 0;
+    for (int step = e.top_pow2 >> 1; step >= 1; step >>= 1) c += (T[c + step - 1] < x) ? step : 0;
+    c += (T[c] < x) ? 1 : 0;
+    // no knot below x: x is K_1 = 0 (or NaN), the bracket is the first interval and u = 0 + m (x - 0)
+    if (c == 0) return x + 0.0;
+    double lo = T[c - 1], hi = c < e.top_pow2 ? T[c] : dinf();               // A[c-1] < x <= A[c]
+    int64_t lb = c;
+    for (int lv = e.nlev - 2; lv >= 0; --lv) {
+        const double2* nd = reinterpret_cast<const double2*>(e.node[lv] + (lb - 1) * ECDF_NODE);
+        const double2 s = __ldg(nd);                                          // (e3, e6)
+        const int c1 = (s.x < x ? 1 : 0) + (s.y < x ? 1 : 0);
+        const double2 p = __ldg(nd + 1 + c1);                                 // (e1,e2) | (e4,e5) | (e7,e8)
+        const int c2 = (p.x < x ? 1 : 0) + (p.y < x ? 1 : 0);
+        const double lo_s = c1 == 0 ? lo : (c1 == 1 ? s.x : s.y), hi_s = c1 == 0 ? s.x : (c1 == 1 ? s.y : hi);
+        lo = c2 == 0 ? lo_s : (c2 == 1 ? p.x : p.y);
+        hi = c2 == 0 ? p.x : (c2 == 1 ? p.y : hi_s);
+        lb = (lb - 1) * ECDF_STRIDE + 1 + 3 * c1 + c2;
     }
-    int64_t j = lb > 0 ? lb - 1 : 0;                                          // k > 1 && (k -= 1)
-    if (j > e.L - 2) j = e.L - 2;
-    const double* K = (top == 0) ? (s_top + e.top_off) : e.lev[0];
-    const double kj = K[j], kj1 = K[j + 1];
+    const int64_t j = lb - 1;                                                 // k > 1 && (k -= 1); lo = K[j], hi = K[j+1]
     const double Lm1 = (double)(e.L - 1);
     const double y0 = (double)j / Lm1, y1 = (double)(j + 1) / Lm1;           // range(0, stop=1, length=L)
-    const double m = (y1 - y0) / (kj1 - kj);
-    return y0 + m * (x - kj);
+    const double m = (y1 - y0) / (hi - lo);
+    return y0 + m * (x - lo);
 }
 #endif
 
@@ -346,17 +322,25 @@ SABC_HD double ecdf_eval_flat(const double* K, int64_t L, double rho) {
 // ------------------------------------------------------------------------------------------------
 // Models (device f_dist).  A model is a struct with
 //   static constexpr int D, S;                         parameters, statistics
+//   static constexpr int FUSED_MIN_BLOCKS, SIM_MIN_BLOCKS, KEY_BITS;   occupancy requests of the fused / simulation kernels, work-list key
 //   static __device__ void sim(th, par, stream, rho)   simulate + distance(s) >= 0
 // ------------------------------------------------------------------------------------------------
 struct ModelPar { double v[MAX_MODEL_PAR]; };
 
 // C1/C5: 1-D Gaussian mean, sufficient-statistic form.  par: ybar_obs, sd_mean (= sigma/sqrt(n))
+#ifndef SABC_GAUSSMEAN_MIN_BLOCKS
+#define SABC_GAUSSMEAN_MIN_BLOCKS 6
+#endif
+#ifndef SABC_GAUSSSAMPLE_MIN_BLOCKS
+#define SABC_GAUSSSAMPLE_MIN_BLOCKS 4
+#endif
 struct GaussMean {
     static constexpr int D = 1, S = 1;
+    static constexpr int FUSED_MIN_BLOCKS = SABC_GAUSSMEAN_MIN_BLOCKS;   // resident CTAs per SM requested for the fused kernel (register cap)
     static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
     static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[1], const ModelPar& mp, Stream& st, double (&rho)[1]) {
-        double z0, z1; normal_pair(st.draw(), z0, z1);
+        const double z0 = normal1(st);
         const double ysim = th[0] + mp.v[1] * z0;
         rho[0] = fabs(ysim - mp.v[0]);
     }
@@ -367,6 +351,7 @@ struct GaussMean {
 template <int D_, int S_>
 struct GaussSample {
     static constexpr int D = D_, S = S_;
+    static constexpr int FUSED_MIN_BLOCKS = SABC_GAUSSSAMPLE_MIN_BLOCKS;
     static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
     static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[D_], const ModelPar& mp, Stream& st, double (&rho)[S_]) {
@@ -374,7 +359,7 @@ struct GaussSample {
         const double sig = D_ >= 2 ? th[D_ - 1] : mp.v[1];
         double s1 = 0.0, s2 = 0.0;
         for (int k = 0; k < n; k += 2) {
-            double z0, z1; normal_pair(st.draw(), z0, z1);
+            double z0, z1; normal2(st, z0, z1);
             double y = th[0] + sig * z0;
             s1 = s1 + y; s2 = s2 + y * y;
             if (k + 1 < n) { y = th[0] + sig * z1; s1 = s1 + y; s2 = s2 + y * y; }
@@ -387,13 +372,14 @@ struct GaussSample {
 // C3: stochastic logistic growth, θ = (r, K, σ), T = 20 points.  par: x0, T, obs[T]
 struct Logistic {
     static constexpr int D = 3, S = 20;
+    static constexpr int FUSED_MIN_BLOCKS = 1;
     static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
     static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[3], const ModelPar& mp, Stream& st, double (&rho)[20]) {
         double x = mp.v[0];
 #pragma unroll
         for (int t = 0; t < S; t += 2) {
-            double z[2]; normal_pair(st.draw(), z[0], z[1]);
+            double z[2]; normal2<false>(st, z[0], z[1]);      // ten unrolled call sites: slow path out of line
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const double grow = (th[0] * x) * (1.0 - x / th[1]);
@@ -412,6 +398,8 @@ struct Logistic {
 // C4: SIR tau-leap, θ = (β, γ, ι, φ).  par: pop, T, tau, obs_total, obs_peak, obs_tpeak
 struct SirTauLeap {
     static constexpr int D = 4, S = 3;
+    static constexpr int FUSED_MIN_BLOCKS = 1;
+    static constexpr int NO_NORMALS = 1;
     static constexpr int SIM_MIN_BLOCKS = SABC_SIR_MIN_BLOCKS;   // 4: cap at 64 registers, 32 warps per SM hide the FP64 latencies
     // similarity key of a proposal for the work-list bucketing: growth rate β−γ (6 bits), initial fraction ι (3), γ (3).
     // Particles of one bucket have similar epidemic curves, so the lanes of a warp meet the same sampler regimes and
@@ -477,6 +465,8 @@ struct SirTauLeap {
 template <int S_>
 struct SirGillespie {
     static constexpr int D = 2, S = S_;
+    static constexpr int FUSED_MIN_BLOCKS = 1;
+    static constexpr int NO_NORMALS = 1;
     static constexpr int SIM_MIN_BLOCKS = 4;
     static constexpr int KEY_BITS = 0;
     SABC_HD static void sim(const double (&th)[2], const ModelPar& mp, Stream& st, double (&rho)[S_]) {

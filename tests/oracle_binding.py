@@ -32,7 +32,7 @@ def model_id(name: str) -> int:
 
 
 def build_oracle() -> str:
-    src = [os.path.join(ORACLE_DIR, f) for f in ("sabc_oracle.c", "sabc_oracle.h", "Makefile")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("sabc_oracle.c", "sabc_oracle.h", "zig_tables.inc", "Makefile")]
     if not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
     return LIB_PATH
@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
             "orc_philox4x32_10": (None, [vp, vp, vp]),
             "orc_normal_pair": (None, [u64, u64, C.POINTER(dbl), C.POINTER(dbl)]),
             "orc_poisson": (i64, [dbl, u64, u32, u64, C.POINTER(u32)]),
+            "orc_zig_normal": (dbl, [u64, u32, u64, C.POINTER(u32)]),
+            "orc_normal_stream": (None, [u64, u32, u64, i32, vp]),
             "orc_treesum": (dbl, [vp, i64]),
             "orc_ecdf_build": (i64, [vp, i64, vp]),
             "orc_ecdf_eval": (None, [vp, i64, vp, i64, vp]),

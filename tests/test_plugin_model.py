@@ -33,13 +33,10 @@ def ar1_reference(theta, par, seed, particle, sweep):
     """the plug-in's arithmetic restated with the oracle's Philox / normal primitives"""
     import oracle_binding as ob
     T = int(par[0]); x = s1 = s2 = sx = 0.0
-    z0, z1 = C.c_double(), C.c_double()
+    zs = np.zeros(2 * ((T + 1) // 2))
+    ob.lib().orc_normal_stream(seed, particle, sweep, zs.size // 2, ob.p(zs))     # the model stream's ziggurat normals, in order
     for t in range(0, T, 2):
-        ctr = (C.c_uint32 * 4)(particle, sweep & 0xffffffff, t // 2, 1 | ((sweep >> 32) << 4)); key = (C.c_uint32 * 2)(seed & 0xffffffff, seed >> 32)
-        out = (C.c_uint32 * 4)()
-        ob.lib().orc_philox4x32_10(ctr, key, out)
-        ob.lib().orc_normal_pair(out[0] | (out[1] << 32), out[2] | (out[3] << 32), C.byref(z0), C.byref(z1))
-        for h, z in enumerate((z0.value, z1.value)):
+        for h, z in enumerate((zs[t], zs[t + 1])):
             if t + h < T:
                 xn = theta[0] * x + theta[1] * z
                 s1 = s1 + xn * x; s2 = s2 + xn * xn; sx = sx + xn; x = xn
