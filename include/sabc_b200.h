@@ -85,6 +85,9 @@ typedef struct sabc_config {
 #define SABC_FLAG_GENERIC_TAIL 32u  /* never use the single-CTA tail kernel of small populations */
 #define SABC_FLAG_MG_REPLICATED 64u /* world_size > 1: every rank holds the whole population and simulates a share of each half-sweep;
                                        bit-identical to one GPU (strict mode for parity studies, memory does not scale) */
+#define SABC_FLAG_MG_STRICT_RESAMPLE 128u /* world_size > 1, sharded: every rank walks all N global resampling draws, so that the resampled
+                                       multiset equals the single-GPU one for the same seed (O(N_global) work and memory per rank);
+                                       default: per-rank counts from ONE shared-seed multinomial draw, O(N / world_size) per rank */
 #define SABC_FLAG_FUSED         4u  /* always use the fused update_half kernel, also for simulation-heavy models */
 
 /* timing of the last sabc_update(), measured with CUDA events on the engine's stream */

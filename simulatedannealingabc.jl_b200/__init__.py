@@ -5,7 +5,7 @@
     sb.update_population(res, model, prior, n_simulation=50_000)
 """
 from . import _lib, models  # noqa: F401
-from ._lib import SABCError, SABC_FLAG_FUSED, SABC_FLAG_GENERIC_TAIL, SABC_FLAG_MG_REPLICATED, SABC_FLAG_NO_GRAPH, SABC_FLAG_NO_PIPELINE, SABC_FLAG_SORT_WORK, SABC_FLAG_TIME_KERNELS  # noqa: F401
+from ._lib import SABCError, SABC_FLAG_FUSED, SABC_FLAG_GENERIC_TAIL, SABC_FLAG_MG_REPLICATED, SABC_FLAG_MG_STRICT_RESAMPLE, SABC_FLAG_NO_GRAPH, SABC_FLAG_NO_PIPELINE, SABC_FLAG_SORT_WORK, SABC_FLAG_TIME_KERNELS  # noqa: F401
 from .api import Engine, SABCresult, SABCstate, sabc, update_population  # noqa: F401
 from .distributions import (Beta, Cauchy, Exponential, Gamma, InverseGamma, Laplace, LogNormal, Normal, Product, Uniform,  # noqa: F401
                             Weibull, product_distribution)

@@ -22,6 +22,7 @@ SABC_FLAG_NO_PIPELINE = 8
 SABC_FLAG_SORT_WORK = 16
 SABC_FLAG_GENERIC_TAIL = 32
 SABC_FLAG_MG_REPLICATED = 64
+SABC_FLAG_MG_STRICT_RESAMPLE = 128
 
 ERR_NAMES = {
     -1: "NSIM_TOO_SMALL", -2: "BAD_V", -3: "BAD_DELTA", -4: "NEG_DISTANCE", -5: "UBAR_ZERO", -6: "BAD_ALGORITHM",

@@ -145,6 +145,7 @@ SABC_D void d_post1_block(const Post1Args& a, int b, double* s_w) {
 }
 static __global__ void __launch_bounds__(CHUNK) k_post1(const Post1Args a) {
     __shared__ double s_w[8];
+    if (a.ds->hold) return;
     d_post1_block(a, blockIdx.x, s_w);
 }
 static __global__ void k_decide(DevState* ds, int S, int64_t n_global, int64_t resample) {
@@ -417,6 +418,7 @@ SABC_D void d_finish(const FinishArgs& a, double* s_um, unsigned long long* s_hi
 static __global__ void k_finish(const FinishArgs a) {
     __shared__ double s_um[MAX_S];
     __shared__ unsigned long long s_hi[MAX_S], s_lo[MAX_S];
+    if (a.ds->hold) return;
     d_finish(a, s_um, s_hi, s_lo);
 }
 
@@ -475,10 +477,11 @@ static __global__ void __launch_bounds__(CHUNK) k_rw_cross_sums(const double* th
     }
 }
 static __global__ void k_rw_means(DevState* ds, const double* sums, int D, int64_t n_global) {
+    if (ds->hold) return;
     if (threadIdx.x < D) ds->mom[threadIdx.x] = sums[threadIdx.x] / (double)n_global;
 }
 static __global__ void k_rw_chol(DevState* ds, const double* sums, int D, int64_t n_global, double beta) {
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x != 0 || ds->hold) return;
     double Sg[MAX_D * MAX_D];
     int p = 0;
     for (int a = 0; a < D; ++a) for (int b = 0; b <= a; ++b, ++p) {
@@ -498,7 +501,7 @@ static __global__ void k_rw_chol(DevState* ds, const double* sums, int D, int64_
 static __global__ void k_begin(DevState* ds, long long t, long long n_pop, long long checkpoint) {
     ds->t = t; ds->ix = 1; ds->n_pop = n_pop; ds->checkpoint = checkpoint; ds->rec = 0; ds->last_cp = 0;
     for (int j = 0; j < MAX_S; ++j) { ds->u_hi[j] = 0ull; ds->u_lo[j] = 0ull; }
-    ds->n_acc_iter = 0ull; ds->resample_flag = 0;
+    ds->n_acc_iter = 0ull; ds->resample_flag = 0; ds->hold = 0;
     for (int k = 0; k < MAX_SLOTS; ++k) { ds->list_count[k] = 0u; ds->list_cursor[k] = 0u; }
 }
 // Σu limbs of an existing u array (set_population, multi-GPU resampling)

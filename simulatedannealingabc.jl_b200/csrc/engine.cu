@@ -7,6 +7,7 @@
 // sequence is captured once in a CUDA graph and replayed without host round trips.
 #include "ecdf_index.cuh"
 #include "nccl_dyn.h"
+#include "multinomial.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <chrono>
@@ -60,11 +61,20 @@ using namespace sabc;
 // ---------------------------------------------------------------------------------------------
 // engine
 // ---------------------------------------------------------------------------------------------
-struct MgScratch {   // multi-GPU resampling work space
+constexpr int MG_LOOKAHEAD = 4;   // updates the host keeps enqueued ahead of the one whose resampling decision it is waiting for
+struct MgScratch {   // multi-GPU work space
     DevBuf<unsigned long long> wall, F, tsum, toff, scalar;
+    DevBuf<unsigned long long> stats_send, stats_all;   // per-update statistics: this rank's packed record, all ranks' records
     DevBuf<int64_t> src;
     DevBuf<double> sb;
     DevBuf<int> flag;
+    int* hold_slots = nullptr;                          // pinned: `hold` after each of the last MG_LOOKAHEAD enqueued updates
+    cudaEvent_t hold_ev[MG_LOOKAHEAD] = {};
+    bool graph_failed = false;
+    ~MgScratch() {
+        if (hold_slots) cudaFreeHost(hold_slots);
+        for (auto ev : hold_ev) if (ev) cudaEventDestroy(ev);
+    }
 };
 
 struct sabc_engine {
@@ -116,6 +126,7 @@ struct sabc_engine {
 
     // graph
     cudaGraphExec_t graph_exec = nullptr;
+    bool mg_warm = false;      // sharded: one update has run with direct launches (NCCL connections exist), the graph may be captured
 
     // host mirror of SABCstate
     bool initialised = false;
@@ -550,7 +561,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     e->v = c->v; e->delta = c->delta; e->resample = c->resample; e->seed = c->seed; e->flags = c->flags;
     e->ecdf_max_knots = c->ecdf_max_knots;
     if (e->flags & SABC_FLAG_TIME_KERNELS) e->flags |= SABC_FLAG_NO_GRAPH;
-    if (world > 1) e->flags |= SABC_FLAG_NO_GRAPH;
+    if (e->replicated) e->flags |= SABC_FLAG_NO_GRAPH;
     e->split = model->heavy && !(e->flags & SABC_FLAG_FUSED);
     e->sort_work = e->split && model->key_bits > 0 && (e->flags & SABC_FLAG_SORT_WORK);
     e->device = dev; e->model = model;
@@ -603,15 +614,23 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
         int rc = e->comm.init(c->nccl_unique_id, e->rank, world);
         if (rc == 0) rc = mg_warm_p2p(e);
         if (rc) return fail(rc);
-        // work space of the global resampling, allocated once (a cudaMalloc inside the update loop costs tens of ms)
+        // work space of the global resampling, allocated once (a cudaMalloc inside the update loop costs tens of ms): O(N / G),
+        // except for the strict variant, which walks all N global draws on every rank
         if (e->replicated) { *out = e; return 0; }
-        const size_t Ng = (size_t)e->N, Nt = (Ng + TILE - 1) / TILE;
-        cudaError_t ce2 = e->mg.F.alloc(Ng);
-        if (ce2 == cudaSuccess) ce2 = e->mg.src.alloc(Ng);
-        if (ce2 == cudaSuccess) ce2 = e->mg.tsum.alloc(Nt);
-        if (ce2 == cudaSuccess) ce2 = e->mg.toff.alloc(Nt);
+        cudaError_t ce2 = cudaSuccess;
+        if (e->flags & SABC_FLAG_MG_STRICT_RESAMPLE) {
+            const size_t Ng = (size_t)e->N, Nt = (Ng + TILE - 1) / TILE;
+            ce2 = e->mg.F.alloc(Ng);
+            if (ce2 == cudaSuccess) ce2 = e->mg.src.alloc(Ng);
+            if (ce2 == cudaSuccess) ce2 = e->mg.tsum.alloc(Nt);
+            if (ce2 == cudaSuccess) ce2 = e->mg.toff.alloc(Nt);
+        }
         if (ce2 == cudaSuccess) ce2 = e->mg.scalar.alloc(1);
         if (ce2 == cudaSuccess) ce2 = e->mg.flag.alloc(1);
+        if (ce2 == cudaSuccess) ce2 = e->mg.stats_send.alloc((size_t)4 * MAX_S + 1);
+        if (ce2 == cudaSuccess) ce2 = e->mg.stats_all.alloc((size_t)(4 * MAX_S + 1) * world);
+        if (ce2 == cudaSuccess) ce2 = cudaHostAlloc((void**)&e->mg.hold_slots, sizeof(int) * MG_LOOKAHEAD, cudaHostAllocDefault);
+        for (int k = 0; k < MG_LOOKAHEAD && ce2 == cudaSuccess; ++k) ce2 = cudaEventCreateWithFlags(&e->mg.hold_ev[k], cudaEventDisableTiming);
         if (ce2 == cudaSuccess) ce2 = e->mg.sb.alloc((size_t)(e->D + e->S + 1) * (n + n / 4 + 4096));
         if (ce2 != cudaSuccess) return fail(set_error(SABC_ERR_CUDA, "multi-GPU work space allocation failed: %s", cudaGetErrorString(ce2)));
     }
@@ -738,12 +757,58 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
     const bool time_kernels = (e->flags & SABC_FLAG_TIME_KERNELS) != 0;
     int rc = 0;
     const bool piped = (bool)e->pipe_before || (bool)e->pipe_after;
-    if (e->world > 1) {
+    if (e->replicated) {
         SABC_CUDA(cudaEventRecord(ev0, e->stream));
         if (time_kernels) e->kev = &kev;
-        for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) {
-            e->pipe_first = piped && ix == 0; e->pipe_last = piped && ix == n_pop - 1;
-            rc = e->replicated ? rep_iteration(e) : mg_iteration(e);
+        for (int64_t ix = 0; ix < n_pop && rc == 0; ++ix) rc = rep_iteration(e);
+        e->kev = nullptr;
+        SABC_CUDA(cudaEventRecord(ev1, e->stream));
+    } else if (e->world > 1) {
+        // Sharded: the host keeps up to MG_LOOKAHEAD updates enqueued and only looks at the `hold` word each of them leaves
+        // behind (asynchronous copy into pinned memory).  A raised hold means that update's decision asked for a resampling: the
+        // updates behind it ran as no-ops, the host runs the exchange, finishes that update and enqueues the others again.
+        MgScratch& mg = e->mg;
+        const bool use_graph = !(e->flags & SABC_FLAG_NO_GRAPH) && !piped && !mg.graph_failed;
+        SABC_CUDA(cudaEventRecord(ev0, e->stream));
+        if (time_kernels) e->kev = &kev;
+        int64_t ix = 0, done = 0;
+        while (done < n_pop && rc == 0) {
+            while (ix < n_pop && ix - done < MG_LOOKAHEAD && rc == 0) {
+                e->pipe_first = piped && ix == 0; e->pipe_last = piped && ix == n_pop - 1;
+                if (use_graph && e->graph_exec) {
+                    SABC_CUDA(cudaGraphLaunch(e->graph_exec, e->stream));
+                } else if (use_graph && e->mg_warm) {           // NCCL has set its channels up: capture the update once
+                    cudaGraph_t graph = nullptr;
+                    cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+                    if (ce == cudaSuccess) {
+                        rc = mg_enqueue_iteration(e);
+                        ce = cudaStreamEndCapture(e->stream, &graph);
+                        if (rc == 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+                        if (graph) cudaGraphDestroy(graph);
+                    }
+                    if (rc != 0 || ce != cudaSuccess || !e->graph_exec) {   // capture refused (e.g. by the NCCL build): direct launches from now on
+                        cudaGetLastError(); rc = 0; mg.graph_failed = true;
+                        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+                        rc = mg_enqueue_iteration(e);
+                    } else {
+                        SABC_CUDA(cudaGraphLaunch(e->graph_exec, e->stream));
+                    }
+                } else {
+                    rc = mg_enqueue_iteration(e);
+                    e->mg_warm = true;
+                }
+                if (rc) break;
+                SABC_CUDA(cudaMemcpyAsync(&mg.hold_slots[ix % MG_LOOKAHEAD], &ds->hold, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+                SABC_CUDA(cudaEventRecord(mg.hold_ev[ix % MG_LOOKAHEAD], e->stream));
+                ++ix;
+            }
+            if (rc) break;
+            SABC_CUDA(cudaEventSynchronize(mg.hold_ev[done % MG_LOOKAHEAD]));
+            if (mg.hold_slots[done % MG_LOOKAHEAD] != 0) {
+                rc = mg_complete_held_iteration(e);
+                ix = done + 1;
+            }
+            ++done;
         }
         e->kev = nullptr; e->pipe_first = e->pipe_last = false;
         SABC_CUDA(cudaEventRecord(ev1, e->stream));

@@ -31,6 +31,10 @@ struct DevState {
     long long ix, n_pop, checkpoint, rec, last_cp; // position inside the current update() call
     long long n_accept, n_resampling;
     int resample_flag, error_flag;
+    // sharded multi-GPU: a global resampling is due.  The host runs the exchange; until it has, the rest of this update and every
+    // update enqueued behind it are no-ops (each kernel of the iteration returns at once), so the host never has to wait for the
+    // trigger before it enqueues the next update (multi_gpu.inl)
+    int hold, hold_pad;
     unsigned int list_count[MAX_SLOTS], list_cursor[MAX_SLOTS];   // split path: work-list length / fetch cursor per (half, sub-range)
 };
 
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(CHUNK, M::FUSED_MIN_BLOCKS) update_half_kernel
     __shared__ ZigEntry s_zig[256];
 
     const int tid = threadIdx.x;
+    if (a.ds->hold) return;
     for (int k = tid; k < 2 * S + 1; k += CHUNK) s_acc[k] = 0ull;
     if (PROP == PROP_RW) for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k];
     const uint32_t zig = stage_zig(s_zig);
@@ -366,6 +371,7 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, cons
     __shared__ double s_chol[PROP == PROP_RW ? D * D : 1];
     __shared__ ZigEntry s_zig[PROP == PROP_STRETCH ? 1 : 256];
     const int tid = threadIdx.x, lane = tid & 31;
+    if (a.ds->hold) return;
     if (PROP == PROP_RW) for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k];
     const uint32_t zig = PROP == PROP_STRETCH ? 0u : stage_zig(s_zig);
     __syncthreads();
@@ -415,6 +421,7 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
     constexpr int D = M::D, S = M::S;
     extern __shared__ __align__(128) double s_top[];
     __shared__ ZigEntry s_zig[model_draws_normals<M>::value ? 256 : 1];
+    if (a.ds->hold) return;
     const uint32_t zig = model_draws_normals<M>::value ? stage_zig(s_zig) : 0u;
     stage_ecdf_top(a.ecdf, S, s_top);
     __syncthreads();
@@ -515,6 +522,7 @@ static __global__ void __launch_bounds__(CHUNK) stats_kernel(PopView pop, int64_
     __shared__ unsigned long long s_acc[2 * MAX_S];
     __shared__ double s_w[8];
     const int tid = threadIdx.x;
+    if (ds->hold) return;
     for (int k = tid; k < 2 * S; k += CHUNK) s_acc[k] = 0ull;
     __syncthreads();
     const int64_t n_groups = (n + CHUNK - 1) / CHUNK;

@@ -105,45 +105,16 @@ static int mg_warm_p2p(sabc_engine* e) {
     return 0;
 }
 
-// exact global multinomial resampling over all ranks (resample_population, :124-137)
-static int mg_resample(sabc_engine* e) {
+// the surplus exchange: rank g's packed selection occupies the global slots [C_g, C_g + c_g), rank d owns [d n, (d+1) n);
+// only what crosses a slice boundary travels (grouped ncclSend/ncclRecv), then the statistics of the new population
+static int mg_exchange_selection(sabc_engine* e, const std::vector<int64_t>& counts, int64_t sb_ld) {
     MgScratch& s = e->mg;
     NcclApi* nc = nccl_api();
     const int G = e->world, me = e->rank;
-    const int64_t n = e->n_local, N = e->N;
+    const int64_t n = e->n_local;
     DevState* ds = e->b_ds.p;
-    const int64_t n_tiles = (n + TILE - 1) / TILE;
-    const int g_tiles = (int)std::min<int64_t>(n_tiles, (int64_t)e->n_sm * 8);
-    // local weights and prefix sums
-    k_weights<<<g_tiles, CHUNK, 0, e->stream>>>(e->pop, n, e->S, e->delta, ds, e->b_q.p, e->b_tile_sum.p, 1);
-    k_scan_tiles<<<1, 1024, 0, e->stream>>>(e->b_tile_sum.p, n_tiles, e->b_tile_off.p, &ds->w_total, ds, 1);
-    k_prefix<<<g_tiles, CHUNK, 0, e->stream>>>(e->b_q.p, n, e->b_tile_off.p, ds, 1);
-    SABC_CUDA(cudaGetLastError());
-    std::vector<unsigned long long> w(G), cnt(G);
-    SABC_TRY(mg_allgather_u64_host(e, &ds->w_total, w.data()));
-    unsigned long long W = 0, my_off = 0;
-    for (int g = 0; g < G; ++g) { if (g == me) my_off = W; W += w[g]; }
-    if (W == 0) return set_error(SABC_ERR_INVALID, "all resampling weights are zero");
-    // every rank walks the same N global draws and keeps its own
-    SABC_CUDA(s.F.ensure((size_t)N)); SABC_CUDA(s.src.ensure((size_t)N));
-    const int64_t N_tiles = (N + TILE - 1) / TILE;
-    SABC_CUDA(s.tsum.ensure((size_t)N_tiles)); SABC_CUDA(s.toff.ensure((size_t)N_tiles)); SABC_CUDA(s.scalar.ensure(1));
-    const int g_all = (int)std::min<int64_t>((N + CHUNK - 1) / CHUNK, (int64_t)e->n_sm * 8);
-    const int g_alltiles = (int)std::min<int64_t>(N_tiles, (int64_t)e->n_sm * 8);
-    k_mg_mark<<<g_all, CHUNK, 0, e->stream>>>(N, W, my_off, w[me], e->b_q.p, n, e->seed, (uint32_t)e->n_resampling, s.F.p, s.src.p);
-    k_tile_sums<<<g_alltiles, CHUNK, 0, e->stream>>>(s.F.p, N, s.tsum.p);
-    k_scan_tiles<<<1, 1024, 0, e->stream>>>(s.tsum.p, N_tiles, s.toff.p, s.scalar.p, ds, 1);
-    k_prefix<<<g_alltiles, CHUNK, 0, e->stream>>>(s.F.p, N, s.toff.p, ds, 1);
-    SABC_CUDA(cudaGetLastError());
-    SABC_TRY(mg_allgather_u64_host(e, s.scalar.p, cnt.data()));
-    const int64_t c_me = (int64_t)cnt[me];
     const int nf = e->D + e->S + 1;
-    const int64_t sb_ld = std::max<int64_t>(c_me, 1);
-    SABC_CUDA(s.sb.ensure((size_t)nf * sb_ld));
-    k_mg_pack<<<g_all, CHUNK, 0, e->stream>>>(e->pop, e->D, e->S, N, s.F.p, s.src.p, s.sb.p, sb_ld);
-    SABC_CUDA(cudaGetLastError());
-    // exchange: the selected particles of rank g occupy global slots [C_g, C_g + c_g); rank d owns [d n, (d+1) n)
-    std::vector<int64_t> counts(cnt.begin(), cnt.end()), s_off(G), s_cnt(G), r_off(G), r_cnt(G);
+    std::vector<int64_t> s_off(G), s_cnt(G), r_off(G), r_cnt(G);
     SABC_TRY(sabc_mg_exchange_plan(counts.data(), G, n, me, s_off.data(), s_cnt.data(), r_off.data(), r_cnt.data()));
     auto field_dst = [&](int f) -> double* {
         if (f < e->D) return e->tmp.theta + (int64_t)f * e->tmp.ld;
@@ -173,27 +144,151 @@ static int mg_resample(sabc_engine* e) {
     return 0;
 }
 
-// one population update on this rank's slice
-static int mg_iteration(sabc_engine* e) {
+// strict variant (SABC_FLAG_MG_STRICT_RESAMPLE): every rank evaluates the same N global variates against the all-gathered weight
+// totals and keeps the draws that land in its own range, so the resampled MULTISET equals the single-GPU one for the same seed
+// (tests/test_gpu_multi.py); O(N_global) work and memory per rank
+static int mg_resample_strict(sabc_engine* e, const std::vector<unsigned long long>& w) {
+    MgScratch& s = e->mg;
+    const int G = e->world, me = e->rank;
+    const int64_t n = e->n_local, N = e->N;
     DevState* ds = e->b_ds.p;
+    unsigned long long W = 0, my_off = 0;
+    for (int g = 0; g < G; ++g) { if (g == me) my_off = W; W += w[g]; }
+    std::vector<unsigned long long> cnt(G);
+    SABC_CUDA(s.F.ensure((size_t)N)); SABC_CUDA(s.src.ensure((size_t)N));
+    const int64_t N_tiles = (N + TILE - 1) / TILE;
+    SABC_CUDA(s.tsum.ensure((size_t)N_tiles)); SABC_CUDA(s.toff.ensure((size_t)N_tiles)); SABC_CUDA(s.scalar.ensure(1));
+    const int g_all = (int)std::min<int64_t>((N + CHUNK - 1) / CHUNK, (int64_t)e->n_sm * 8);
+    const int g_alltiles = (int)std::min<int64_t>(N_tiles, (int64_t)e->n_sm * 8);
+    k_mg_mark<<<g_all, CHUNK, 0, e->stream>>>(N, W, my_off, w[me], e->b_q.p, n, e->seed, (uint32_t)e->n_resampling, s.F.p, s.src.p);
+    k_tile_sums<<<g_alltiles, CHUNK, 0, e->stream>>>(s.F.p, N, s.tsum.p);
+    k_scan_tiles<<<1, 1024, 0, e->stream>>>(s.tsum.p, N_tiles, s.toff.p, s.scalar.p, ds, 1);
+    k_prefix<<<g_alltiles, CHUNK, 0, e->stream>>>(s.F.p, N, s.toff.p, ds, 1);
+    SABC_CUDA(cudaGetLastError());
+    SABC_TRY(mg_allgather_u64_host(e, s.scalar.p, cnt.data()));
+    const int64_t sb_ld = std::max<int64_t>((int64_t)cnt[me], 1);
+    SABC_CUDA(s.sb.ensure((size_t)(e->D + e->S + 1) * sb_ld));
+    k_mg_pack<<<g_all, CHUNK, 0, e->stream>>>(e->pop, e->D, e->S, N, s.F.p, s.src.p, s.sb.p, sb_ld);
+    SABC_CUDA(cudaGetLastError());
+    return mg_exchange_selection(e, std::vector<int64_t>(cnt.begin(), cnt.end()), sb_ld);
+}
+
+// c_me draws among this rank's own particles, fused with the packing of the selected particles (field-major, draw order).
+// Draw t of this rank is global draw C_me + t of the resampling: its own Philox block.
+static __global__ void __launch_bounds__(CHUNK) k_mg_draw_pack(PopView pop, int D, int S, int64_t c_me, int64_t C_me, unsigned long long w_me,
+                                                        const unsigned long long* P, int64_t n_local, uint64_t seed, uint32_t rc,
+                                                        double* sb, int64_t sb_ld) {
+    for (int64_t t = (int64_t)blockIdx.x * CHUNK + threadIdx.x; t < c_me; t += (int64_t)gridDim.x * CHUNK) {
+        const uint64_t k = (uint64_t)(C_me + t);
+        const U64x2 w = philox4x32_10((uint32_t)k, rc, (uint32_t)(k >> 32), KIND_RESAMPLE, (uint32_t)seed, (uint32_t)(seed >> 32));
+        int64_t src = upper_bound_u64(P, n_local, mulhi64(w.a, w_me));
+        if (src >= n_local) src = n_local - 1;
+        for (int c = 0; c < D; ++c) sb[c * sb_ld + t] = pop.theta[c * pop.ld + src];
+        for (int j = 0; j < S; ++j) sb[(D + j) * sb_ld + t] = pop.u[j * pop.ld + src];
+        sb[(D + S) * sb_ld + t] = pop.lp[src];
+    }
+}
+
+// exact global multinomial resampling over all ranks (resample_population, :124-137): the per-rank counts are ONE multinomial
+// draw from a shared seed (multinomial.h), each rank then draws its c_g particles locally -- O(N / G) work and memory per rank
+static int mg_resample(sabc_engine* e) {
+    MgScratch& s = e->mg;
+    const int G = e->world, me = e->rank;
+    const int64_t n = e->n_local, N = e->N;
+    DevState* ds = e->b_ds.p;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int g_tiles = (int)std::min<int64_t>(n_tiles, (int64_t)e->n_sm * 8);
+    // local weights and prefix sums
+    k_weights<<<g_tiles, CHUNK, 0, e->stream>>>(e->pop, n, e->S, e->delta, ds, e->b_q.p, e->b_tile_sum.p, 1);
+    k_scan_tiles<<<1, 1024, 0, e->stream>>>(e->b_tile_sum.p, n_tiles, e->b_tile_off.p, &ds->w_total, ds, 1);
+    k_prefix<<<g_tiles, CHUNK, 0, e->stream>>>(e->b_q.p, n, e->b_tile_off.p, ds, 1);
+    SABC_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> w(G);
+    SABC_TRY(mg_allgather_u64_host(e, &ds->w_total, w.data()));
+    unsigned long long W = 0;
+    for (int g = 0; g < G; ++g) W += w[g];
+    if (W == 0) return set_error(SABC_ERR_INVALID, "all resampling weights are zero");
+    if (e->flags & SABC_FLAG_MG_STRICT_RESAMPLE) return mg_resample_strict(e, w);
+    std::vector<int64_t> counts(G);
+    multinomial_split(N, w.data(), G, e->seed, (uint32_t)e->n_resampling, counts.data());
+    int64_t C_me = 0;
+    for (int g = 0; g < me; ++g) C_me += counts[g];
+    const int64_t c_me = counts[me], sb_ld = std::max<int64_t>(c_me, 1);
+    SABC_CUDA(s.sb.ensure((size_t)(e->D + e->S + 1) * sb_ld));
+    if (c_me > 0) {
+        const int grid = (int)std::min<int64_t>((c_me + CHUNK - 1) / CHUNK, (int64_t)e->n_sm * 8);
+        k_mg_draw_pack<<<grid, CHUNK, 0, e->stream>>>(e->pop, e->D, e->S, c_me, C_me, w[me], e->b_q.p, n, e->seed, (uint32_t)e->n_resampling,
+                                                      s.sb.p, sb_ld);
+        SABC_CUDA(cudaGetLastError());
+    }
+    return mg_exchange_selection(e, counts, sb_ld);
+}
+
+// the per-update statistics of this rank, packed for ONE all-gather: [u_hi[S] | u_lo[S] | n_acc | rho_sum half 0 [S] | half 1 [S]]
+static __global__ void k_mg_pack_stats(const DevState* ds, int S, unsigned long long* out) {
+    const int t = threadIdx.x;
+    if (t < S) {
+        out[t] = ds->u_hi[t]; out[S + t] = ds->u_lo[t];
+        out[2 * S + 1 + t] = (unsigned long long)__double_as_longlong(ds->rho_sum[0][t]);
+        out[3 * S + 1 + t] = (unsigned long long)__double_as_longlong(ds->rho_sum[1][t]);
+    }
+    if (t == 0) out[2 * S] = ds->n_acc_iter;
+}
+// every rank reduces the gathered statistics in rank order (integer sums exact, rho sums in one fixed order: identical on all
+// ranks), then takes the decision of :334-343.  A due resampling raises `hold`: see DevState.
+static __global__ void k_mg_decide(DevState* ds, const unsigned long long* all, int G, int S, int64_t n_global, int64_t resample) {
+    if (ds->hold) return;
+    const int W = 4 * S + 1, t = threadIdx.x;
+    if (t < S) {
+        unsigned long long hi = 0, lo = 0;
+        double r0 = 0.0, r1 = 0.0;
+        for (int g = 0; g < G; ++g) {
+            hi += all[g * W + t]; lo += all[g * W + S + t];
+            const double a = __longlong_as_double((long long)all[g * W + 2 * S + 1 + t]), b = __longlong_as_double((long long)all[g * W + 3 * S + 1 + t]);
+            r0 = g == 0 ? a : r0 + a; r1 = g == 0 ? b : r1 + b;
+        }
+        ds->u_hi[t] = hi; ds->u_lo[t] = lo; ds->rho_sum[0][t] = r0; ds->rho_sum[1][t] = r1;
+    }
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long na = 0;
+        for (int g = 0; g < G; ++g) na += all[g * W + 2 * S];
+        ds->n_acc_iter = na;
+        post1_decide(ds, S, n_global, resample);
+        ds->hold = ds->resample_flag;
+    }
+}
+static __global__ void k_mg_release(DevState* ds) { ds->hold = 0; }
+
+// one population update on this rank's slice, enqueue only: no host round trip, so a run of updates is queued ahead of the GPU
+// (and replayed as a CUDA graph).  One collective per update; RandomWalk adds the two moment all-reduces of update_proposal!.
+static int mg_enqueue_iteration(sabc_engine* e) {
+    DevState* ds = e->b_ds.p;
+    MgScratch& s = e->mg;
+    const int W = 4 * e->S + 1;
     SABC_TRY(enqueue_sweeps(e));
     SABC_TRY(launch_post1(e, 0));
-    SABC_TRY(mg_reduce_iteration_sums(e));
-    SABC_TRY(mg_allreduce_f64(e, &ds->rho_sum[0][0], 2 * MAX_S));
-    k_decide<<<1, 32, 0, e->stream>>>(ds, e->S, e->N, e->resample);
+    k_mg_pack_stats<<<1, 32, 0, e->stream>>>(ds, e->S, s.stats_send.p);
     SABC_CUDA(cudaGetLastError());
-    int flag = 0;
-    SABC_CUDA(cudaMemcpyAsync(&flag, &ds->resample_flag, sizeof flag, cudaMemcpyDeviceToHost, e->stream));
-    SABC_CUDA(cudaStreamSynchronize(e->stream));
-    if (flag) {
-        const auto t0 = std::chrono::steady_clock::now();
-        SABC_TRY(mg_resample(e));
-        SABC_CUDA(cudaStreamSynchronize(e->stream));
-        e->timing.resample_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        e->timing.resample_events += 1;
-    }
+    SABC_NCCL(nccl_api()->AllGather(s.stats_send.p, s.stats_all.p, (size_t)W, ncclUint64, e->comm.comm, e->stream));
+    k_mg_decide<<<1, 32, 0, e->stream>>>(ds, s.stats_all.p, e->world, e->S, e->N, e->resample);
+    SABC_CUDA(cudaGetLastError());
     SABC_TRY(launch_update_proposal_mg(e));
     SABC_TRY(launch_finish(e));
+    return 0;
+}
+// the host half of an update whose decision raised `hold`: the global resampling, then the rest of that update
+static int mg_complete_held_iteration(sabc_engine* e) {
+    const auto t0 = std::chrono::steady_clock::now();
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    SABC_TRY(mg_resample(e));
+    k_mg_release<<<1, 1, 0, e->stream>>>(e->b_ds.p);
+    SABC_CUDA(cudaGetLastError());
+    SABC_TRY(launch_update_proposal_mg(e));
+    SABC_TRY(launch_finish(e));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    e->timing.resample_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    e->timing.resample_events += 1;
     return 0;
 }
 
