@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SABC_ABI_VERSION 1
+#define SABC_ABI_VERSION 2   /* 2: sabc_config ends with n_gpus, gpu_ids; sabc_timing ends with d2h_bytes */
 
 /* error classes; the first block mirrors the reference's error() sites */
 #define SABC_OK                 0
@@ -76,6 +76,12 @@ typedef struct sabc_config {
      * keeps K rank-uniform quantiles of the positive prior distances (plus 0 and 1.5 max) and fits into shared memory as a whole;
      * an approximation of order 1/K that the oracle reproduces when given the same K. */
     int32_t  ecdf_max_knots;
+    /* ABI 2.  n_gpus > 1: ONE process drives n_gpus devices through this handle (the reference's caller is one Julia session,
+     * src/SimulatedAnnealingABC.jl:451-460): the library forms an in-process communicator, GPU r owns the particle slice
+     * [r N/n_gpus, (r+1) N/n_gpus), host arrays are the GLOBAL N x d / N x s matrices.  gpu_ids: n_gpus device ordinals, NULL = 0 .. n_gpus-1.
+     * rank / world_size / nccl_unique_id / device are ignored then.  Same bits as the process-per-GPU mode with the same seed. */
+    int32_t  n_gpus;
+    const int32_t* gpu_ids;
 } sabc_config;
 
 #define SABC_FLAG_NO_GRAPH      1u  /* launch kernels directly instead of replaying a CUDA graph */
@@ -100,6 +106,7 @@ typedef struct sabc_timing {
     double  host_ms;           /* host-buffer call: first byte up to last byte down, CUDA events */
     double  resample_ms;       /* multi-GPU: host wall time inside the global resampling exchanges */
     int64_t resample_events;
+    int64_t d2h_bytes;         /* host-buffer call: bytes of the result download (only the rows that changed unless a resampling fell into the call) */
 } sabc_timing;
 
 /* ---- lifetime ---- */

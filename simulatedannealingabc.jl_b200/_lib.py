@@ -45,13 +45,14 @@ class Config(C.Structure):
         ("resample", C.c_int64), ("seed", C.c_uint64), ("model_name", C.c_char_p), ("model_par", c_double_p),
         ("n_model_par", C.c_int32), ("device", C.c_int32), ("prior_kind", c_int32_p), ("prior_par", c_double_p),
         ("rank", C.c_int32), ("world_size", C.c_int32), ("nccl_unique_id", C.c_void_p), ("flags", C.c_uint32), ("ecdf_max_knots", C.c_int32),
+        ("n_gpus", C.c_int32), ("gpu_ids", c_int32_p),
     ]
 
 
 class Timing(C.Structure):
     _fields_ = [("update_ms", C.c_double), ("kernel_ms", C.c_double), ("kernel_launches", C.c_int64),
                 ("total_launches", C.c_int64), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("host_ms", C.c_double),
-                ("resample_ms", C.c_double), ("resample_events", C.c_int64)]
+                ("resample_ms", C.c_double), ("resample_events", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 # every symbol include/sabc_b200.h declares: name -> (restype, argtypes)

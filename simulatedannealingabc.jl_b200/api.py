@@ -31,7 +31,8 @@ class Engine:
 
     def __init__(self, model: DeviceModel, prior: Distribution, *, n_particles: int, algorithm: str, proposal: Proposal,
                  resample: int, v: float, delta: float, seed: int = 0x5ABC, device: int = -1, rank: int = 0,
-                 world_size: int = 1, nccl_unique_id: bytes | None = None, flags: int = 0, ecdf_max_knots: int = 0):
+                 world_size: int = 1, nccl_unique_id: bytes | None = None, flags: int = 0, ecdf_max_knots: int = 0,
+                 n_gpus: int = 0, gpu_ids=None):
         comps = prior.components()
         if len(comps) != model.n_para:
             raise _lib.SABCError(-20, f"prior has {len(comps)} components but model '{model.name}' has {model.n_para} parameters")
@@ -59,6 +60,10 @@ class Engine:
         cfg.nccl_unique_id = C.cast(self._uid, C.c_void_p) if self._uid is not None else None
         cfg.flags = flags
         cfg.ecdf_max_knots = int(ecdf_max_knots)
+        # one process, several GPUs: the handle shards the particles itself (host arrays stay the global N x d / N x s matrices)
+        self._gpu_ids = np.ascontiguousarray(gpu_ids, dtype=np.int32) if gpu_ids is not None else None
+        cfg.n_gpus = int(n_gpus) if self._gpu_ids is None else int(self._gpu_ids.size)
+        cfg.gpu_ids = self._gpu_ids.ctypes.data_as(_lib.c_int32_p) if self._gpu_ids is not None else None
         self._h = C.c_void_p()
         _lib.check(_lib.lib().sabc_create(C.byref(self._h), C.byref(cfg)))
         nl, off = C.c_int64(), C.c_int64()
@@ -287,7 +292,7 @@ def sabc(f_dist, prior: Distribution, *args, n_particles: int = 100, n_simulatio
          algorithm: str = "single_eps", proposal: Proposal | None = None, resample: int | None = None,
          v: float = 1.0, delta: float = 0.1, checkpoint_history: int = 1, show_progressbar: bool = False,
          show_checkpoint=math.inf, type: str | None = None, seed: int = 0x5ABC, device: int = -1, comm=None,
-         flags: int = 0, ecdf_max_knots: int = 0, **kwargs) -> SABCresult:
+         flags: int = 0, ecdf_max_knots: int = 0, n_gpus: int = 0, gpu_ids=None, **kwargs) -> SABCresult:
     """sabc(f_dist, prior, args...; kw...)  -- src/SimulatedAnnealingABC.jl:451-492."""
     if "δ" in kwargs:
         delta = kwargs.pop("δ")
@@ -310,7 +315,7 @@ def sabc(f_dist, prior: Distribution, *args, n_particles: int = 100, n_simulatio
     rank, world, uid = _distributed_setup(comm)
     eng = Engine(f_dist, prior, n_particles=n_particles, algorithm=algorithm, proposal=proposal, resample=resample,
                  v=v, delta=delta, seed=seed, device=device, rank=rank, world_size=world, nccl_unique_id=uid, flags=flags,
-                 ecdf_max_knots=ecdf_max_knots)
+                 ecdf_max_knots=ecdf_max_knots, n_gpus=n_gpus, gpu_ids=gpu_ids)
     eng.init()                                                                        # :470-473
     res = SABCresult(eng, algorithm)
     n_sim_remaining = n_simulation - res.state.n_simulation                           # :478

@@ -15,6 +15,7 @@
 #include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace sabc {
@@ -78,6 +79,10 @@ struct MgScratch {   // multi-GPU work space
 };
 
 struct sabc_engine {
+    // single-process multi-GPU handle: the engine is a group of per-GPU engines (ranks of an in-process communicator), every call
+    // fans out to them on one host thread per GPU (group.inl); a leaf engine has no children
+    std::vector<sabc_engine*> children;
+    bool is_group() const { return !children.empty(); }
     MgScratch mg;
     // configuration
     int64_t N = 0, n_local = 0, offset = 0;
@@ -109,6 +114,9 @@ struct sabc_engine {
     DevBuf<double> b_sp_theta, b_sp_lp, b_sp_lf;      // split path work list
     DevBuf<uint32_t> b_sp_idx, b_sp_key, b_sp_perm;
     DevBuf<unsigned int> b_sp_hist, b_sp_off;
+    DevBuf<unsigned char> b_dirty;                     // host-buffer calls: rows accepted since the last upload
+    DevBuf<double> b_pack; DevBuf<unsigned int> b_pack_cnt;
+    double* h_pack = nullptr; unsigned int* h_pack_cnt = nullptr; int64_t pack_cap = 0;   // pinned staging of the compact download
     bool sort_work = false;
     bool split = false;
     int grid_simacc = 0, bps_simacc = 0;
@@ -136,6 +144,8 @@ struct sabc_engine {
     sabc_timing timing{};
 
     ~sabc_engine() {
+        if (h_pack) cudaFreeHost(h_pack);
+        if (h_pack_cnt) cudaFreeHost(h_pack_cnt);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (auto* b : ecdf_bufs) delete b;
         comm.destroy();
@@ -468,6 +478,15 @@ extern "C" int sabc_mg_exchange_plan(const int64_t* counts, int32_t world, int64
 
 #include "multi_gpu.inl"
 
+extern "C" {
+static int get_population_ld(sabc_engine* e, double* theta, double* u, double* rho, int64_t ld);
+static int set_population_ld(sabc_engine* e, const double* theta, const double* u, const double* rho, int64_t ld, const double* eps,
+                             const int64_t counters[4]);
+static int update_host_ld(sabc_engine* e, double* theta, double* u, double* rho, int64_t ld, double* eps, int64_t counters[4],
+                          int64_t n_simulation, int64_t checkpoint_history);
+}
+#include "group.inl"
+
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -517,6 +536,7 @@ int sabc_model_info(const char* name, int32_t* n_para, int32_t* n_stats) {
 int sabc_create(sabc_engine** out, const sabc_config* c) {
     if (!out || !c) return set_error(SABC_ERR_INVALID, "null argument");
     *out = nullptr;
+    if (c->n_gpus > 1) return group_create(out, c);
     if (!(c->algorithm == SABC_ALG_SINGLE_EPS || c->algorithm == SABC_ALG_MULTI_EPS))
         return set_error(SABC_ERR_BAD_ALGORITHM, "Argument `algorithm` must be :multi_eps or :single_eps");
     if (c->proposal < 0 || c->proposal > 2) return set_error(SABC_ERR_BAD_PROPOSAL, "unknown proposal %d", c->proposal);
@@ -640,6 +660,7 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
 
 int sabc_destroy(sabc_engine* e) {
     if (!e) return 0;
+    if (e->is_group()) return group_destroy(e);
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     delete e;
@@ -648,6 +669,7 @@ int sabc_destroy(sabc_engine* e) {
 
 int sabc_set_tuning(sabc_engine* e, double v, double delta, int64_t resample, int32_t proposal, const double* prop_par) {
     if (!e || !prop_par) return set_error(SABC_ERR_INVALID, "null argument");
+    if (e->is_group()) return group_set_tuning(e, v, delta, resample, proposal, prop_par);
     if (proposal < 0 || proposal > 2) return set_error(SABC_ERR_BAD_PROPOSAL, "unknown proposal %d", proposal);
     if (proposal == SABC_PROP_RW && !(prop_par[0] > 0.0 && prop_par[0] <= 1.0))
         return set_error(SABC_ERR_BAD_PROPOSAL, "Mixing parameter `β` must be between zero and one.");
@@ -668,6 +690,7 @@ int sabc_local_particles(sabc_engine* e, int64_t* n_local, int64_t* offset) {
 // initialization()  src/SimulatedAnnealingABC.jl:151-227
 int sabc_init(sabc_engine* e) {
     if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (e->is_group()) return group_init(e);
     SABC_CUDA(cudaSetDevice(e->device));
     const int64_t n = e->n_local;
     DevState* ds = e->b_ds.p;
@@ -737,6 +760,7 @@ int sabc_init(sabc_engine* e) {
 // update_population!()  src/SimulatedAnnealingABC.jl:251-402
 int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history) {
     if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (e->is_group()) return group_update(e, n_simulation, checkpoint_history);
     if (!e->initialised) return set_error(SABC_ERR_STATE, "sabc_update before sabc_init / sabc_set_population");
     if (!(e->v > 0.0)) return set_error(SABC_ERR_BAD_V, "Annealing speed `v` must be positive.");
     if (!(e->delta > 0.0)) return set_error(SABC_ERR_BAD_DELTA, "Resamping intensity `δ` must be positive.");
@@ -857,92 +881,211 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
     return 0;
 }
 
-int sabc_get_population(sabc_engine* e, double* theta, double* u, double* rho) {
-    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+// Copies of the row range [r0, r1) of a column-major matrix with ncol columns between host and device; the two sides may have
+// different leading dimensions (a single-process multi-GPU handle passes slices of the caller's global arrays)
+static int copy_rows(double* dst, int64_t dst_ld, const double* src, int64_t src_ld, int ncol, int64_t r0, int64_t r1,
+                     cudaMemcpyKind kind, cudaStream_t st) {
+    if (r1 <= r0) return 0;
+    if (dst_ld == src_ld && r0 == 0 && r1 == dst_ld) { SABC_CUDA(cudaMemcpyAsync(dst, src, (size_t)dst_ld * ncol * sizeof(double), kind, st)); return 0; }
+    // one strided copy: ncol rows of (r1-r0) doubles, pitch = one column
+    SABC_CUDA(cudaMemcpy2DAsync(dst + r0, (size_t)dst_ld * sizeof(double), src + r0, (size_t)src_ld * sizeof(double),
+                                (size_t)(r1 - r0) * sizeof(double), (size_t)ncol, kind, st));
+    return 0;
+}
+
+static int get_population_ld(sabc_engine* e, double* theta, double* u, double* rho, int64_t ld) {
     SABC_CUDA(cudaSetDevice(e->device));
-    const size_t n = (size_t)e->n_local;
-    if (theta) SABC_CUDA(cudaMemcpyAsync(theta, e->pop.theta, n * e->D * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    if (u) SABC_CUDA(cudaMemcpyAsync(u, e->pop.u, n * e->S * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    if (rho) SABC_CUDA(cudaMemcpyAsync(rho, e->pop.rho, n * e->S * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    const int64_t n = e->n_local;
+    if (theta) SABC_TRY(copy_rows(theta, ld, e->pop.theta, n, e->D, 0, n, cudaMemcpyDeviceToHost, e->stream));
+    if (u) SABC_TRY(copy_rows(u, ld, e->pop.u, n, e->S, 0, n, cudaMemcpyDeviceToHost, e->stream));
+    if (rho) SABC_TRY(copy_rows(rho, ld, e->pop.rho, n, e->S, 0, n, cudaMemcpyDeviceToHost, e->stream));
     SABC_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
-int sabc_set_population(sabc_engine* e, const double* theta, const double* u, const double* rho, const double* eps,
-                        const int64_t counters[4]) {
-    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
-    if (!theta || !u || !rho || !eps || !counters) return set_error(SABC_ERR_INVALID, "null argument");
-    if (e->top_doubles == 0) return set_error(SABC_ERR_STATE, "no ECDF tables: call sabc_init or sabc_set_ecdf for every statistic first");
-    SABC_CUDA(cudaSetDevice(e->device));
-    const size_t n = (size_t)e->n_local;
-    SABC_CUDA(cudaMemcpyAsync(e->pop.theta, theta, n * e->D * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    SABC_CUDA(cudaMemcpyAsync(e->pop.u, u, n * e->S * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    SABC_CUDA(cudaMemcpyAsync(e->pop.rho, rho, n * e->S * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, 0, (int64_t)n, e->D, e->prior);
+static int set_state_scalars(sabc_engine* e, const double* eps, const int64_t counters[4]) {
     for (int k = 0; k < e->n_eps; ++k) e->eps[k] = eps[k];
     e->n_simulation = counters[0]; e->n_accept = counters[1]; e->n_resampling = counters[2]; e->n_population_updates = counters[3];
     SABC_CUDA(cudaMemcpyAsync(&e->b_ds.p->eps[0], e->eps, sizeof(double) * e->n_eps, cudaMemcpyHostToDevice, e->stream));
     k_set_counters<<<1, 1, 0, e->stream>>>(e->b_ds.p, e->n_accept, e->n_resampling);
     SABC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int set_population_ld(sabc_engine* e, const double* theta, const double* u, const double* rho, int64_t ld, const double* eps,
+                             const int64_t counters[4]) {
+    if (!theta || !u || !rho || !eps || !counters) return set_error(SABC_ERR_INVALID, "null argument");
+    if (e->top_doubles == 0) return set_error(SABC_ERR_STATE, "no ECDF tables: call sabc_init or sabc_set_ecdf for every statistic first");
+    SABC_CUDA(cudaSetDevice(e->device));
+    const int64_t n = e->n_local;
+    SABC_TRY(copy_rows(e->pop.theta, n, theta, ld, e->D, 0, n, cudaMemcpyHostToDevice, e->stream));
+    SABC_TRY(copy_rows(e->pop.u, n, u, ld, e->S, 0, n, cudaMemcpyHostToDevice, e->stream));
+    SABC_TRY(copy_rows(e->pop.rho, n, rho, ld, e->S, 0, n, cudaMemcpyHostToDevice, e->stream));
+    k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, 0, n, e->D, e->prior);
+    SABC_TRY(set_state_scalars(e, eps, counters));
     SABC_CUDA(cudaStreamSynchronize(e->stream));
     e->initialised = true;
     return 0;
 }
 
-// Column-wise copies of the row range [r0, r1) of a column-major n x ncol matrix
-static int copy_rows(double* dst, const double* src, int64_t n, int ncol, int64_t r0, int64_t r1, cudaMemcpyKind kind, cudaStream_t st) {
-    if (r1 <= r0) return 0;
-    if (r0 == 0 && r1 == n) { SABC_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * ncol * sizeof(double), kind, st)); return 0; }
-    // one strided copy: ncol rows of (r1-r0) doubles, pitch = one column
-    SABC_CUDA(cudaMemcpy2DAsync(dst + r0, (size_t)n * sizeof(double), src + r0, (size_t)n * sizeof(double),
-                                (size_t)(r1 - r0) * sizeof(double), (size_t)ncol, kind, st));
+int sabc_get_population(sabc_engine* e, double* theta, double* u, double* rho) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (e->is_group()) return group_get_population(e, theta, u, rho);
+    return get_population_ld(e, theta, u, rho, e->n_local);
+}
+
+int sabc_set_population(sabc_engine* e, const double* theta, const double* u, const double* rho, const double* eps,
+                        const int64_t counters[4]) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (e->is_group()) return group_set_population(e, theta, u, rho, eps, counters);
+    return set_population_ld(e, theta, u, rho, e->n_local, eps, counters);
+}
+
+// Rows whose particle accepted during a host-buffer call, packed as [row index, theta.., u.., rho..] for a compact download:
+// one population update changes only the accepted rows (about a(1 - prior rejects) of them), so shipping all three matrices
+// home again would move several times the bytes that changed.
+static __global__ void __launch_bounds__(CHUNK) k_compact_dirty(PopView pop, int64_t n, int D, int S, double* pack, unsigned int cap,
+                                                         unsigned int* count) {
+    const int lane = threadIdx.x & 31, w = 1 + D + 2 * S;
+    const int64_t n_round = (n + 31) / 32 * 32;
+    for (int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * CHUNK) {
+        const bool d = i < n && pop.dirty[i] != 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, d);
+        unsigned base = 0;
+        if (lane == 0 && mask) base = atomicAdd(count, (unsigned)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (d) {
+            const unsigned pos = base + __popc(mask & ((1u << lane) - 1u));
+            if (pos < cap) {
+                double* row = pack + (size_t)pos * w;
+                row[0] = (double)i;
+                for (int c = 0; c < D; ++c) row[1 + c] = pop.theta[c * pop.ld + i];
+                for (int j = 0; j < S; ++j) { row[1 + D + j] = pop.u[j * pop.ld + i]; row[1 + D + S + j] = pop.rho[j * pop.ld + i]; }
+            }
+        }
+    }
+}
+
+// bring the result of a host-buffer call home: only the rows that changed when no resampling fell into the call (and the
+// packed rows fit the staging buffer), everything otherwise
+static int download_result(sabc_engine* e, double* theta, double* u, double* rho, int64_t ld, bool resampled) {
+    const int64_t n = e->n_local;
+    const int w = 1 + e->D + 2 * e->S;
+    e->timing.d2h_bytes = 0;
+    if (!resampled && e->pop.dirty && e->pack_cap > 0) {
+        SABC_CUDA(cudaMemsetAsync(e->b_pack_cnt.p, 0, sizeof(unsigned int), e->s_out));
+        const int grid = (int)std::min<int64_t>((n + CHUNK - 1) / CHUNK, (int64_t)e->n_sm * 8);
+        k_compact_dirty<<<grid, CHUNK, 0, e->s_out>>>(e->pop, n, e->D, e->S, e->b_pack.p, (unsigned)e->pack_cap, e->b_pack_cnt.p);
+        SABC_CUDA(cudaGetLastError());
+        unsigned int cnt = 0;
+        SABC_CUDA(cudaMemcpyAsync(&e->h_pack_cnt[0], e->b_pack_cnt.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->s_out));
+        SABC_CUDA(cudaStreamSynchronize(e->s_out));
+        cnt = e->h_pack_cnt[0];
+        if ((int64_t)cnt <= e->pack_cap) {
+            if (cnt > 0) {
+                SABC_CUDA(cudaMemcpyAsync(e->h_pack, e->b_pack.p, (size_t)cnt * w * sizeof(double), cudaMemcpyDeviceToHost, e->s_out));
+                SABC_CUDA(cudaStreamSynchronize(e->s_out));
+                // scatter on the host, a few threads: the rows are disjoint
+                const int D = e->D, S = e->S;
+                const double* pk = e->h_pack;
+                auto work = [=](unsigned lo, unsigned hi) {
+                    for (unsigned k = lo; k < hi; ++k) {
+                        const double* row = pk + (size_t)k * w;
+                        const int64_t i = (int64_t)row[0];
+                        for (int c = 0; c < D; ++c) theta[c * ld + i] = row[1 + c];
+                        for (int j = 0; j < S; ++j) { u[j * ld + i] = row[1 + D + j]; rho[j * ld + i] = row[1 + D + S + j]; }
+                    }
+                };
+                const unsigned nt = cnt < 20000u ? 1u : 4u;
+                std::vector<std::thread> th;
+                for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, (unsigned)((uint64_t)cnt * t / nt), (unsigned)((uint64_t)cnt * (t + 1) / nt));
+                work(0, (unsigned)((uint64_t)cnt / nt));
+                for (auto& t : th) t.join();
+            }
+            e->timing.d2h_bytes = (int64_t)cnt * w * (int64_t)sizeof(double) + 4;
+            return 0;
+        }
+    }
+    SABC_TRY(copy_rows(theta, ld, e->pop.theta, n, e->D, 0, n, cudaMemcpyDeviceToHost, e->s_out));
+    SABC_TRY(copy_rows(u, ld, e->pop.u, n, e->S, 0, n, cudaMemcpyDeviceToHost, e->s_out));
+    SABC_TRY(copy_rows(rho, ld, e->pop.rho, n, e->S, 0, n, cudaMemcpyDeviceToHost, e->s_out));
+    SABC_CUDA(cudaStreamSynchronize(e->s_out));
+    e->timing.d2h_bytes = (int64_t)n * (e->D + 2 * e->S) * (int64_t)sizeof(double);
     return 0;
 }
 
-// update_population!(::SABCresult) with the result held in host buffers.  For large slices the transfers are pipelined
-// with the two half-sweeps: the first sweep starts as soon as theta and the first half of u, rho have arrived, the rest
-// of the upload overlaps it; the first half is downloaded while the second sweep runs.
-int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, double* eps, int64_t counters[4],
-                     int64_t n_simulation, int64_t checkpoint_history) {
-    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+// update_population!(::SABCresult) with the result held in host buffers (leading dimension ld).  The upload is issued in order
+// of need and pipelined with the half-sweeps: the first sweep starts as soon as theta of the second half (its partners) and the
+// first sub-range of the first half have arrived, the rest of the upload overlaps it.  Only the rows that changed travel home.
+static int update_host_ld(sabc_engine* e, double* theta, double* u, double* rho, int64_t ld, double* eps, int64_t counters[4],
+                          int64_t n_simulation, int64_t checkpoint_history) {
     if (!theta || !u || !rho || !eps || !counters) return set_error(SABC_ERR_INVALID, "null argument");
     SABC_CUDA(cudaSetDevice(e->device));
     const int64_t n = e->n_local, h0 = n / 2, n_pop = n_simulation / e->N;
     const bool pipe = n_pop >= 1 && n >= 32768 && !(e->flags & SABC_FLAG_NO_PIPELINE) && !e->replicated && e->top_doubles > 0 &&
                       e->v > 0.0 && e->delta > 0.0;
+    if (!e->s_in) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    if (!e->s_out) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    // dirty-row tracking and the staging buffers of the compact download (first host call)
+    const bool compact = !(e->flags & SABC_FLAG_NO_PIPELINE) && !e->replicated;
+    if (compact && !e->b_dirty.p) {
+        const int w = 1 + e->D + 2 * e->S;
+        e->pack_cap = n / 2 + 1024;
+        SABC_CUDA(e->b_dirty.alloc((size_t)n)); SABC_CUDA(e->b_pack.alloc((size_t)e->pack_cap * w)); SABC_CUDA(e->b_pack_cnt.alloc(1));
+        SABC_CUDA(cudaHostAlloc((void**)&e->h_pack, (size_t)e->pack_cap * w * sizeof(double), cudaHostAllocDefault));
+        SABC_CUDA(cudaHostAlloc((void**)&e->h_pack_cnt, sizeof(unsigned int) * 4, cudaHostAllocDefault));
+    }
     cudaEvent_t a, b, c, d;
     SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b)); SABC_CUDA(cudaEventCreate(&c)); SABC_CUDA(cudaEventCreate(&d));
-    auto cleanup = [&] { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); };
-    int rc = 0;
-    if (!pipe) {
-        SABC_CUDA(cudaEventRecord(a, e->stream));
-        rc = sabc_set_population(e, theta, u, rho, eps, counters);
-        if (!rc) { SABC_CUDA(cudaEventRecord(b, e->stream)); rc = sabc_update(e, n_simulation, checkpoint_history); }
-        if (!rc) { SABC_CUDA(cudaEventRecord(c, e->stream)); rc = sabc_get_population(e, theta, u, rho); }
-        if (!rc) rc = sabc_get_state(e, eps, counters);
+    std::vector<cudaEvent_t> evs;
+    auto cleanup = [&] { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); for (auto ev : evs) cudaEventDestroy(ev); };
+    auto finish_call = [&](int rc, const sabc_timing& t_upd, int64_t n_res_before) -> int {
         if (!rc) {
-            SABC_CUDA(cudaEventRecord(d, e->stream));
+            SABC_CUDA(cudaEventRecord(c, e->s_out));
+            rc = download_result(e, theta, u, rho, ld, e->n_resampling != n_res_before);
+            if (!rc) rc = sabc_get_state(e, eps, counters);
+        }
+        if (!rc) {
+            SABC_CUDA(cudaEventRecord(d, e->s_out));
             SABC_CUDA(cudaEventSynchronize(d));
+            SABC_CUDA(cudaStreamSynchronize(e->s_in));
             float t1 = 0, t2 = 0, t3 = 0;
             cudaEventElapsedTime(&t1, a, b); cudaEventElapsedTime(&t2, c, d); cudaEventElapsedTime(&t3, a, d);
-            e->timing.h2d_ms = t1; e->timing.d2h_ms = t2; e->timing.host_ms = t3;
+            const int64_t d2h = e->timing.d2h_bytes;
+            e->timing = t_upd;
+            e->timing.h2d_ms = t1; e->timing.d2h_ms = t2; e->timing.host_ms = t3; e->timing.d2h_bytes = d2h;
+        } else {
+            cudaStreamSynchronize(e->s_in); cudaStreamSynchronize(e->s_out);
         }
         cleanup();
         return rc;
+    };
+    int rc = 0;
+    if (compact) {       // from the first host call on every accept marks its row (one byte); the flags are cleared per call
+        SABC_CUDA(cudaMemsetAsync(e->b_dirty.p, 0, (size_t)n, e->stream));
+        if (!e->pop.dirty) {
+            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // captured without the pointer
+            e->pop.dirty = e->b_dirty.p;
+        }
     }
-    if (!e->s_in) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
-    if (!e->s_out) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    if (!pipe) {
+        SABC_CUDA(cudaEventRecord(a, e->s_in));
+        SABC_CUDA(cudaStreamWaitEvent(e->stream, a, 0));
+        rc = set_population_ld(e, theta, u, rho, ld, eps, counters);
+        const int64_t n_res_before = e->n_resampling;
+        SABC_CUDA(cudaEventRecord(b, e->stream));
+        if (!rc) rc = sabc_update(e, n_simulation, checkpoint_history);
+        return finish_call(rc, e->timing, n_res_before);
+    }
     // 2 sub-ranges per half measured best on B200 (4.70 ms vs 4.85 at 1, 5.9 at 3, 6.8 at 4 per C4 step): the simulation
     // kernel needs ~150 k items to fill the GPU, smaller sub-sweeps only add latency-bound tails.  SABC_PIPE_NSUB overrides.
     const int nsub_env = getenv("SABC_PIPE_NSUB") ? atoi(getenv("SABC_PIPE_NSUB")) : 2;
     const int nsub = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nsub_env, (int)MAX_SUB), h0 / 32768));
-    cudaEvent_t evT1, evUp[2][MAX_SUB], evDn[2][MAX_SUB];
-    std::vector<cudaEvent_t> evs;
+    cudaEvent_t evT1, evUp[2][MAX_SUB];
     auto mk = [&](cudaEvent_t& ev) { cudaError_t r = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); if (r == cudaSuccess) evs.push_back(ev); return r; };
-    auto cleanup2 = [&] { for (auto ev : evs) cudaEventDestroy(ev); cleanup(); };
-    SABC_CUDA(mk(evT1));
-    for (int h = 0; h < 2; ++h) for (int j = 0; j < nsub; ++j) { SABC_CUDA(mk(evUp[h][j])); SABC_CUDA(mk(evDn[h][j])); }
-    const auto H2D = cudaMemcpyHostToDevice; const auto D2H = cudaMemcpyDeviceToHost;
+    if (mk(evT1) != cudaSuccess) { cleanup(); return set_error(SABC_ERR_CUDA, "event creation failed"); }
+    for (int h = 0; h < 2; ++h) for (int j = 0; j < nsub; ++j) if (mk(evUp[h][j]) != cudaSuccess) { cleanup(); return set_error(SABC_ERR_CUDA, "event creation failed"); }
+    const auto H2D = cudaMemcpyHostToDevice;
     auto rows = [&](int half, int sub, int64_t& r0, int64_t& r1) {       // absolute row range of a sub-range
         int64_t off, an, t0, t1;
         halves(e, half, off, an, t0, t1);
@@ -952,28 +1095,24 @@ int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, doub
     // upload order = order of need: theta of the second half (partners of the first sweep), then per sub-range of the first
     // half its rows of theta, u, rho; then the rows of u, rho of the second half
     SABC_CUDA(cudaEventRecord(a, e->s_in));
-    rc = copy_rows(e->pop.theta, theta, n, e->D, h0, n, H2D, e->s_in);
+    rc = copy_rows(e->pop.theta, n, theta, ld, e->D, h0, n, H2D, e->s_in);
     if (!rc) { SABC_CUDA(cudaEventRecord(evT1, e->s_in)); }
     for (int half = 0; half < 2 && !rc; ++half)
         for (int j = 0; j < nsub && !rc; ++j) {
             int64_t r0, r1; rows(half, j, r0, r1);
-            if (half == 0) rc = copy_rows(e->pop.theta, theta, n, e->D, r0, r1, H2D, e->s_in);
-            if (!rc) rc = copy_rows(e->pop.u, u, n, e->S, r0, r1, H2D, e->s_in);
-            if (!rc) rc = copy_rows(e->pop.rho, rho, n, e->S, r0, r1, H2D, e->s_in);
+            if (half == 0) rc = copy_rows(e->pop.theta, n, theta, ld, e->D, r0, r1, H2D, e->s_in);
+            if (!rc) rc = copy_rows(e->pop.u, n, u, ld, e->S, r0, r1, H2D, e->s_in);
+            if (!rc) rc = copy_rows(e->pop.rho, n, rho, ld, e->S, r0, r1, H2D, e->s_in);
             if (!rc) { SABC_CUDA(cudaEventRecord(evUp[half][j], e->s_in)); }
         }
-    if (rc) { cudaStreamSynchronize(e->s_in); cleanup2(); return rc; }
+    if (rc) { cudaStreamSynchronize(e->s_in); cleanup(); return rc; }
     SABC_CUDA(cudaEventRecord(b, e->s_in));
     // state scalars; cached log-prior of the second half as soon as its theta is there
     SABC_CUDA(cudaStreamWaitEvent(e->stream, evT1, 0));
     k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, h0, n, e->D, e->prior);
-    for (int k = 0; k < e->n_eps; ++k) e->eps[k] = eps[k];
-    e->n_simulation = counters[0]; e->n_accept = counters[1]; e->n_resampling = counters[2]; e->n_population_updates = counters[3];
-    SABC_CUDA(cudaMemcpyAsync(&e->b_ds.p->eps[0], e->eps, sizeof(double) * e->n_eps, H2D, e->stream));
-    k_set_counters<<<1, 1, 0, e->stream>>>(e->b_ds.p, e->n_accept, e->n_resampling);
-    SABC_CUDA(cudaGetLastError());
+    SABC_TRY(set_state_scalars(e, eps, counters));
     if (e->proposal == PROP_RW)        // update_proposal! (:284) reads the whole population before the first sweep
-        SABC_CUDA(cudaStreamWaitEvent(e->stream, evUp[0][nsub - 1], 0));
+        SABC_CUDA(cudaStreamWaitEvent(e->stream, evUp[1][nsub - 1], 0));
     e->initialised = true;
     const int64_t n_res_before = e->n_resampling;
     e->pipe_nsub = nsub;
@@ -985,40 +1124,16 @@ int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, doub
         }
         return 0;
     };
-    // after its (sub-)sweep of the last update a row range is final (unless a resampling follows): it goes home while
-    // the next sub-ranges are being simulated
-    e->pipe_after = [&](int half, int sub) -> int {
-        int64_t r0, r1; rows(half, sub, r0, r1);
-        SABC_CUDA(cudaEventRecord(evDn[half][sub], e->stream));
-        SABC_CUDA(cudaStreamWaitEvent(e->s_out, evDn[half][sub], 0));
-        SABC_TRY(copy_rows(theta, e->pop.theta, n, e->D, r0, r1, D2H, e->s_out));
-        SABC_TRY(copy_rows(u, e->pop.u, n, e->S, r0, r1, D2H, e->s_out));
-        return copy_rows(rho, e->pop.rho, n, e->S, r0, r1, D2H, e->s_out);
-    };
     rc = sabc_update(e, n_simulation, checkpoint_history);          // blocks until the updates are done
-    e->pipe_before = nullptr; e->pipe_after = nullptr; e->pipe_nsub = 1;
-    const sabc_timing t_upd = e->timing;
-    if (!rc) {
-        SABC_CUDA(cudaEventRecord(c, e->s_out));
-        if (e->n_resampling != n_res_before) {                      // theta, u of every row changed after the sweeps
-            rc = copy_rows(theta, e->pop.theta, n, e->D, 0, n, D2H, e->s_out);
-            if (!rc) rc = copy_rows(u, e->pop.u, n, e->S, 0, n, D2H, e->s_out);
-        }
-        if (!rc) rc = sabc_get_state(e, eps, counters);
-    }
-    if (!rc) {
-        SABC_CUDA(cudaEventRecord(d, e->s_out));
-        SABC_CUDA(cudaEventSynchronize(d));
-        SABC_CUDA(cudaStreamSynchronize(e->s_in));
-        float t1 = 0, t2 = 0, t3 = 0;
-        cudaEventElapsedTime(&t1, a, b); cudaEventElapsedTime(&t2, c, d); cudaEventElapsedTime(&t3, a, d);
-        e->timing = t_upd;
-        e->timing.h2d_ms = t1; e->timing.d2h_ms = t2; e->timing.host_ms = t3;
-    } else {
-        cudaStreamSynchronize(e->s_in); cudaStreamSynchronize(e->s_out);
-    }
-    cleanup2();
-    return rc;
+    e->pipe_before = nullptr; e->pipe_nsub = 1;
+    return finish_call(rc, e->timing, n_res_before);
+}
+
+int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, double* eps, int64_t counters[4],
+                     int64_t n_simulation, int64_t checkpoint_history) {
+    if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (e->is_group()) return group_update_host(e, theta, u, rho, eps, counters, n_simulation, checkpoint_history);
+    return update_host_ld(e, theta, u, rho, e->n_local, eps, counters, n_simulation, checkpoint_history);
 }
 
 int sabc_get_state(sabc_engine* e, double* eps, int64_t counters[4]) {
@@ -1029,17 +1144,20 @@ int sabc_get_state(sabc_engine* e, double* eps, int64_t counters[4]) {
 }
 int sabc_history_len(sabc_engine* e, int64_t* n_records) {
     if (!e || !n_records) return set_error(SABC_ERR_INVALID, "null argument");
+    if (e->is_group()) e = e->children[0];
     *n_records = (int64_t)(e->eps_h.size() / (size_t)e->n_eps);
     return 0;
 }
 int sabc_get_history(sabc_engine* e, double* eps_h, double* u_h, double* rho_h) {
     if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (e->is_group()) e = e->children[0];
     if (eps_h) std::memcpy(eps_h, e->eps_h.data(), e->eps_h.size() * sizeof(double));
     if (u_h) std::memcpy(u_h, e->u_h.data(), e->u_h.size() * sizeof(double));
     if (rho_h) std::memcpy(rho_h, e->rho_h.data(), e->rho_h.size() * sizeof(double));
     return 0;
 }
 int sabc_get_ecdf(sabc_engine* e, int32_t stat, double* knots_out, int64_t* L) {
+    if (e && e->is_group()) e = e->children[0];
     if (!e || stat < 0 || stat >= e->S || e->h_ecdf[stat].L == 0) return set_error(SABC_ERR_INVALID, "no such ECDF");
     if (L) *L = e->h_ecdf[stat].L;
     if (knots_out) {
@@ -1051,6 +1169,7 @@ int sabc_get_ecdf(sabc_engine* e, int32_t stat, double* knots_out, int64_t* L) {
 int sabc_set_ecdf(sabc_engine* e, int32_t stat, const double* knots, int64_t L) {
     if (!e || stat < 0 || stat >= e->S || !knots || L < 3) return set_error(SABC_ERR_INVALID, "bad ECDF argument");
     if (knots[0] != 0.0) return set_error(SABC_ERR_INVALID, "knots[0] must be 0 (values = [0; sort(x); ...], src/cdf_estimators.jl:33)");
+    if (e->is_group()) return group_set_ecdf(e, stat, knots, L);
     SABC_CUDA(cudaSetDevice(e->device));
     auto* b = new DevBuf<double>();
     e->ecdf_bufs.push_back(b);
@@ -1070,6 +1189,7 @@ int sabc_get_timing(sabc_engine* e, sabc_timing* out) {
 }
 int sabc_update_kernel_info(sabc_engine* e, int* grid, int* block, int* smem_bytes, int* blocks_per_sm) {
     if (!e) return set_error(SABC_ERR_INVALID, "null engine");
+    if (e->is_group()) e = e->children[0];
     if (grid) *grid = e->split ? e->grid_simacc : e->grid_update;
     if (block) *block = CHUNK;
     if (smem_bytes) *smem_bytes = (int)e->smem_update;

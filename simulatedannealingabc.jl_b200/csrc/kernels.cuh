@@ -162,6 +162,7 @@ struct PopView {                 // structure-of-arrays particle state of one GP
     double* rho;                 // [S][ld]
     double* lp;                  // [ld] cached logpdf(prior, θ_i)   (reference recomputes it, :318)
     int64_t ld;
+    unsigned char* dirty;        // [ld] or nullptr: set when the row accepts (host-buffer calls download only those rows)
 };
 
 struct UpdateArgs {
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(CHUNK, M::FUSED_MIN_BLOCKS) update_half_kernel
 #pragma unroll
                 for (int j = 0; j < S; ++j) { a.pop.u[j * ld + gi] = up[j]; a.pop.rho[j * ld + gi] = rp[j]; }
                 a.pop.lp[gi] = lpp;
+                if (a.pop.dirty) a.pop.dirty[gi] = 1;
             } else {
 #pragma unroll
                 for (int j = 0; j < S; ++j) { up[j] = a.pop.u[j * ld + gi]; rp[j] = a.pop.rho[j * ld + gi]; }
@@ -466,6 +468,7 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
 #pragma unroll
                 for (int j = 0; j < S; ++j) { a.pop.u[j * ld + gi] = up[j]; a.pop.rho[j * ld + gi] = rp[j]; }
                 a.pop.lp[gi] = lpp;
+                if (a.pop.dirty) a.pop.dirty[gi] = 1;
                 n_acc++;
             }
         }

@@ -10,6 +10,7 @@ using SimulatedAnnealingABC
 import SimulatedAnnealingABC: sabc, update_population!, SABCresult, SABCstate, Proposal,
                               DifferentialEvolution, StretchMove, RandomWalk
 using Distributions: Distribution, Uniform, Normal, Exponential, LogNormal, Gamma, Beta, Cauchy, Laplace, Weibull, InverseGamma, Product, params
+import Distributions
 
 const libsabc = get(ENV, "SABC_B200_LIB", joinpath(@__DIR__, "..", "libsabc_b200.so"))
 
@@ -20,7 +21,9 @@ struct SabcConfig
     model_name::Cstring; model_par::Ptr{Float64}; n_model_par::Int32; device::Int32
     prior_kind::Ptr{Int32}; prior_par::Ptr{Float64}
     rank::Int32; world_size::Int32; nccl_unique_id::Ptr{Cvoid}; flags::UInt32; ecdf_max_knots::Int32
+    n_gpus::Int32; gpu_ids::Ptr{Int32}                                  # ABI 2: one Julia session drives n_gpus devices
 end
+# field order, offsets and sizes are compared with offsetof()/sizeof() of include/sabc_b200.h by tests/test_julia_layout.py
 
 struct SABCDeviceError <: Exception
     code::Int; msg::String
@@ -46,6 +49,10 @@ sir_tauleap(obs_total, obs_peak, obs_tpeak; pop=1e5, n_steps=50, τ=1.0) =
 # ---- plug-in encodings ----
 prior_components(p::Union{Uniform,Normal,Exponential,LogNormal,Gamma,Beta,Cauchy,Laplace,Weibull,InverseGamma}) = [p]
 prior_components(p::Product) = collect(p.v)
+# Distributions >= 0.25.72 returns a ProductDistribution from product_distribution(...); older versions a Product
+if isdefined(Distributions, :ProductDistribution)
+    prior_components(p::Distributions.ProductDistribution) = collect(p.dists)
+end
 prior_kind(::Uniform) = Int32(0); prior_kind(::Normal) = Int32(1); prior_kind(::Exponential) = Int32(2); prior_kind(::LogNormal) = Int32(3); prior_kind(::Gamma) = Int32(4); prior_kind(::Beta) = Int32(5)
 prior_kind(::Cauchy) = Int32(6); prior_kind(::Laplace) = Int32(7); prior_kind(::Weibull) = Int32(8); prior_kind(::InverseGamma) = Int32(9)
 prior_params(c) = (p = params(c); length(p) == 2 ? (p[1], p[2]) : (p[1], 0.0))
@@ -59,7 +66,7 @@ end
 destroy!(e::Engine) = (e.h != C_NULL && ccall((:sabc_destroy, libsabc), Cint, (Ptr{Cvoid},), e.h); e.h = C_NULL; nothing)
 
 function Engine(model::DeviceModel, prior::Distribution; n_particles, algorithm, proposal::Proposal, resample, v, δ,
-                seed=0x5ABC, device=-1, ecdf_max_knots=0)
+                seed=0x5ABC, device=-1, ecdf_max_knots=0, n_gpus=0, gpu_ids::Vector{Int32}=Int32[])
     comps = prior_components(prior)
     length(comps) == model.n_para || error("prior has $(length(comps)) components, model $(model.name) has $(model.n_para) parameters")
     kinds = Int32[prior_kind(c) for c in comps]
@@ -67,10 +74,12 @@ function Engine(model::DeviceModel, prior::Distribution; n_particles, algorithm,
     pcode, ppars = proposal_code(proposal)
     alg = algorithm == :multi_eps ? Int32(1) : Int32(0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve kinds ppar model begin
+    isempty(gpu_ids) || (n_gpus = length(gpu_ids))
+    GC.@preserve kinds ppar model gpu_ids begin
         cfg = SabcConfig(n_particles, model.n_para, model.n_stats, alg, pcode, ppars, v, δ, resample, seed,
                          Base.unsafe_convert(Cstring, model.name), pointer(model.par), length(model.par), device,
-                         pointer(kinds), pointer(ppar), 0, 1, C_NULL, 0, ecdf_max_knots)
+                         pointer(kinds), pointer(ppar), 0, 1, C_NULL, 0, ecdf_max_knots,
+                         n_gpus, isempty(gpu_ids) ? Ptr{Int32}(C_NULL) : pointer(gpu_ids))
         check(ccall((:sabc_create, libsabc), Cint, (Ref{Ptr{Cvoid}}, Ref{SabcConfig}), h, cfg))
     end
     e = Engine(h[], model, n_particles, model.n_para, model.n_stats, algorithm == :multi_eps ? model.n_stats : 1)
@@ -100,12 +109,15 @@ Device method of `SimulatedAnnealingABC.sabc` (src/SimulatedAnnealingABC.jl:451-
 """
 function sabc(f_dist::DeviceModel, prior::Distribution; n_particles=100, n_simulation=10_000, algorithm=:single_eps,
               proposal::Proposal=DifferentialEvolution(n_para=length(prior)), resample=2 * n_particles, v=1.0, δ=0.1,
-              checkpoint_history=1, show_progressbar=false, show_checkpoint=Inf, type=nothing, seed=0x5ABC, device=-1)
+              checkpoint_history=1, show_progressbar=false, show_checkpoint=Inf, type=nothing, seed=0x5ABC, device=-1,
+              n_gpus=0, gpu_ids::Vector{Int32}=Int32[])
     type === nothing || (algorithm = Dict(:single => :single_eps, :multi => :multi_eps, :hybrid => :single_eps)[type])
     (algorithm == :multi_eps || algorithm == :single_eps) ||
         error("Argument `algorithm` must be :multi_eps or :single_eps, not `$algorithm`!")
     n_simulation < n_particles && error("`n_simulation = $n_simulation` is too small for $n_particles particles.")
-    e = Engine(f_dist, prior; n_particles, algorithm, proposal, resample, v, δ, seed, device)
+    # n_gpus > 1: this one session drives all of them; the particles are sharded inside the library, the arrays returned below and
+    # passed to update_population! stay the global N x d / N x s matrices
+    e = Engine(f_dist, prior; n_particles, algorithm, proposal, resample, v, δ, seed, device, n_gpus, gpu_ids)
     check(ccall((:sabc_init, libsabc), Cint, (Ptr{Cvoid},), e.h))                       # initialization()
     n_sim_remaining = n_simulation - n_particles
     n_sim_remaining < n_particles && @warn "`n_simulation` too small to update all particles!"

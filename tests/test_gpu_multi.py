@@ -64,6 +64,9 @@ for name, N, n_upd, prop in (("gauss_mean", 4000 * world, 30, "de"), ("gauss_sam
     assert np.all(np.isfinite(all_th)) and np.all((all_u >= 0) & (all_u <= 1 + 1e-15))
     assert np.all(eps > 0) and np.all(eps < 1)
     report[name + "_" + prop] = {"eps": eps.tolist(), "counters": cnt.tolist(), "mean_u": all_u.mean(axis=0).tolist()}
+    if rank == 0 and os.environ.get("SABC_REF_OUT"):       # reference for the single-process handle (compared by the pytest process)
+        np.savez(os.path.join(os.environ["SABC_REF_OUT"], f"{name}_{prop}.npz"), theta=all_th, u=all_u, rho=all_r, eps=eps, counters=cnt,
+                 eps_h=eh, u_h=uh, rho_h=rh)
     eng.close()
 
 # replicated ("strict") mode: whole population on every rank, each simulates a share -> bit-identical to the oracle
@@ -182,6 +185,7 @@ def test_sharded_population(gpu, world, tmp_path):
     env = dict(os.environ, SABC_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), str(script)]
+    env["SABC_REF_OUT"] = str(tmp_path)
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     if r.returncode != 0:
         lines = [l for l in (r.stdout + r.stderr).splitlines() if any(k in l for k in ("Error", "assert", "Traceback", "File \"/", "rank"))]
@@ -189,3 +193,58 @@ def test_sharded_population(gpu, world, tmp_path):
     assert r.stdout.count("OK") == world
     rep = [l for l in r.stdout.splitlines() if l.startswith("REPORT ")]
     assert rep and json.loads(rep[0][7:])
+    single_process_handle_checks(world, tmp_path)
+
+
+def single_process_handle_checks(world, ref_dir):
+    """sabc_config.n_gpus: ONE process drives `world` GPUs through one handle (the caller the reference's surface describes).  The
+    handle runs the per-GPU engines of the process-per-GPU mode on one host thread each, so for the same seed it must reproduce the
+    torchrun run bit for bit -- population (global arrays), eps, counters, histories -- and its replicated mode the oracle."""
+    import numpy as np
+    import oracle_binding as ob
+    import sabc_b200 as sb
+    from helpers import model_cases
+    for name, n_per, n_upd, prop in (("gauss_mean", 4000, 30, "de"), ("gauss_sample_d2s2", 3000, 15, "stretch"), ("sir_tauleap", 2048, 10, "de"),
+                                     ("gauss_sample_d2s2", 2000, 10, "rw")):
+        ref = np.load(os.path.join(str(ref_dir), f"{name}_{prop}.npz"))
+        model, prior = model_cases()[name]
+        N = n_per * world
+        proposal = {"de": sb.DifferentialEvolution(n_para=model.n_para), "stretch": sb.StretchMove(), "rw": sb.RandomWalk(n_para=model.n_para)}[prop]
+        alg = "multi_eps" if model.n_stats > 1 and name != "sir_tauleap" else "single_eps"
+        eng = sb.Engine(model, prior, n_particles=N, algorithm=alg, proposal=proposal, resample=N // 2, v=1.0, delta=0.1, n_gpus=world)
+        assert eng.n_local == N and eng.offset == 0                     # the handle presents the whole population
+        eng.init(); eng.update(n_upd * N)
+        th, u, r = eng.get_population()
+        assert np.array_equal(th, ref["theta"]) and np.array_equal(u, ref["u"]) and np.array_equal(r, ref["rho"]), (name, prop)
+        eps, cnt = eng.get_state()
+        assert np.array_equal(eps, ref["eps"]) and np.array_equal(cnt, ref["counters"])
+        for a, key in zip(eng.get_history(), ("eps_h", "u_h", "rho_h")):
+            assert np.array_equal(a, ref[key])
+        # host-buffer call on the GLOBAL arrays == device-resident continuation
+        th2, u2, r2, eps2, cnt2 = th.copy(order="F"), u.copy(order="F"), r.copy(order="F"), eps.copy(), cnt.copy()
+        eng.update(3 * N)
+        twin = sb.Engine(model, prior, n_particles=N, algorithm=alg, proposal=proposal, resample=N // 2, v=1.0, delta=0.1, n_gpus=world)
+        for j in range(model.n_stats):
+            twin.set_ecdf(j, eng.get_ecdf(j))
+        twin.update_host(th2, u2, r2, eps2, cnt2, 3 * N)
+        for a, b in zip(eng.get_population(), (th2, u2, r2)):
+            assert np.array_equal(a, b), (name, prop, "update_host through the handle")
+        assert np.array_equal(eng.get_state()[0], eps2) and np.array_equal(eng.get_state()[1], cnt2)
+        eng.close(); twin.close()
+    # replicated (strict) mode through the handle: bit-identical to the oracle
+    model, prior = model_cases()["sir_tauleap"]
+    N = 1250 * world
+    kw = dict(n_particles=N, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=4), resample=N // 8, v=1.0, delta=0.1)
+    eng = sb.Engine(model, prior, n_gpus=world, flags=sb.SABC_FLAG_MG_REPLICATED, **kw)
+    eng.init(); eng.update(8 * N)
+    orc = ob.OracleEngine(model, prior, **kw); orc.init(); orc.update(8 * N)
+    for a, b in zip(eng.get_population(), orc.get_population()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(eng.get_state()[0], orc.get_state()[0]) and np.array_equal(eng.get_state()[1], orc.get_state()[1])
+    eng.close()
+    # the mirrored public surface: sabc(...; n_gpus) from one process
+    f2, p2 = model_cases()["gauss_sample_d2s2"]
+    res = sb.sabc(f2, p2, n_particles=500 * world, n_simulation=5000 * world, algorithm="multi_eps", n_gpus=world)
+    assert res.state.n_population_updates == 9 and res.population.shape == (500 * world, 2) and np.all(res.state.eps < 1)
+    sb.update_population(res, f2, p2, n_simulation=5000 * world)
+    assert res.state.n_population_updates == 19

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", sb._lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (sabc_[a-z0-9_]+)", out))
     assert set(names) <= exported
-    assert lib.sabc_abi_version() == 1
+    assert lib.sabc_abi_version() == 2
 
 
 def test_cuda_code_is_sm_100a():
