@@ -64,7 +64,7 @@ def algorithmic_bytes_per_update(d: int, s: int, accept_frac: float) -> float:
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md): one streaming nvidia-smi process
-    sampling every 50 ms, started before and killed after the region."""
+    sampling every 10 ms, started before the timed region and killed after the end-to-end leg."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -75,14 +75,14 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
         if self.proc is None:
             return
-        time.sleep(0.06)
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -166,6 +166,112 @@ def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, ste
     return steps * n / sec, cores, f"{n} particles x {steps} population updates (same model, prior, proposal) in {sec:.2f} s", 1e3 * sec / steps
 
 
+
+def csrc_digest() -> str:
+    """sha256 over the CUDA sources: stamps the committed ncu counts, so that a number taken from an older kernel is never reported."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "simulatedannealingabc.jl_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".inl", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_counts(key: str):
+    """per-launch counts of the dominant kernel from the committed `ncu --set full` capture (tools/make_kernel_counts.py):
+    DRAM bytes, warp instructions, thread instructions, issue-slot utilisation under ncu.  None if the capture was taken from
+    different kernel sources than the ones this run uses."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_counts.json")))
+        rec = tab["kernels"].get(key)
+        if rec is None:
+            return None, "no capture for this kernel / size"
+        if tab.get("csrc_sha256_16") != csrc_digest():
+            return None, f"capture is stale (taken at csrc {tab.get('csrc_sha256_16')}, running {csrc_digest()})"
+        return rec, tab.get("source")
+    except Exception as ex:
+        return None, f"profiles/r2_kernel_counts.json unreadable ({type(ex).__name__})"
+
+
+def run_config(sb, name, n_particles, steps, warmup, device, flags=0):
+    """one device-resident measurement of another configuration (the `extra` object): (value, ms_per_step, kernel ms, accept fraction)."""
+    model, prior, algorithm, _, desc = workload(name)
+    eng = sb.Engine(model, prior, n_particles=n_particles, algorithm=algorithm, proposal=sb.DifferentialEvolution(n_para=model.n_para),
+                    resample=2 * n_particles, v=1.0, delta=0.1, device=device, flags=sb.SABC_FLAG_TIME_KERNELS | flags)
+    eng.init(); eng.update(warmup * n_particles)
+    c0 = eng.get_state()[1].copy()
+    eng.update(steps * n_particles)
+    t = eng.timing(); c1 = eng.get_state()[1]
+    acc = float(c1[1] - c0[1]) / float(steps * n_particles)
+    out = {"workload": desc, "n_particles": n_particles, "steps": steps, "value": steps * n_particles / (t["update_ms"] * 1e-3),
+           "ms_per_step": t["update_ms"] / steps, "avg_kernel_ms": t["kernel_ms"] / max(t["kernel_launches"], 1), "accept_fraction": acc}
+    d, s_ = model.n_para, model.n_stats
+    peak, _ = measured_peak_hbm()
+    out["hbm_frac_algorithmic"] = algorithmic_bytes_per_update(d, s_, acc) * (n_particles / 2) / (out["avg_kernel_ms"] * 1e-3) / 1e9 / peak
+    eng.close()
+    return out
+
+
+def mg_parity(sb, dist, rank, world, local_rank):
+    """multi-GPU correctness evidence in the driver's own run, OUTSIDE the timed region (the oracle is the checker here):
+    replicated mode against the oracle bit for bit, the invariants that define the sharded mode, and the strict resampling
+    variant against the single-GPU multiset."""
+    import oracle_binding as ob
+    from helpers import model_cases
+    res = {}
+
+    def gather(x):
+        out = [None] * world
+        dist.all_gather_object(out, x)
+        return out
+
+    model, prior = model_cases()["sir_tauleap"]
+    N = 1250 * world
+    kw = dict(n_particles=N, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=4), resample=N // 8, v=1.0, delta=0.1)
+    comm = sb.api._distributed_setup("torch")
+    eng = sb.Engine(model, prior, device=local_rank, rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], flags=sb.SABC_FLAG_MG_REPLICATED, **kw)
+    eng.init(); eng.update(8 * N)
+    orc = ob.OracleEngine(model, prior, **kw); orc.init(); orc.update(8 * N)
+    same = all(np.array_equal(a, b) for a, b in zip(eng.get_population(), orc.get_population())) and \
+        np.array_equal(eng.get_state()[0], orc.get_state()[0]) and np.array_equal(eng.get_state()[1], orc.get_state()[1]) and \
+        all(np.array_equal(a, b) for a, b in zip(eng.get_history(), orc.get_history()))
+    res["replicated_vs_oracle"] = "bit-exact" if all(gather(bool(same))) else "MISMATCH"
+    eng.close(); orc.close()
+
+    model, prior = model_cases()["gauss_sample_d2s2"]
+    N = 4096 * world
+    kw = dict(n_particles=N, algorithm="multi_eps", proposal=sb.DifferentialEvolution(n_para=2), resample=N // 2, v=1.0, delta=0.1, seed=7)
+    comm = sb.api._distributed_setup("torch")
+    eng = sb.Engine(model, prior, device=local_rank, rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], **kw)
+    eng.init(); eng.update(20 * N)
+    th, u, r = eng.get_population()
+    st = gather([eng.get_state()[0].tolist(), eng.get_state()[1].tolist(), [h.tolist() for h in eng.get_history()]])
+    all_u = np.concatenate(gather(u)); all_r = np.concatenate(gather(r))
+    eh, uh, rh = eng.get_history()
+    ok = all(x == st[0] for x in st) and np.allclose(uh[-1], all_u.mean(axis=0), rtol=1e-12, atol=1e-15) and \
+        np.allclose(rh[-1], all_r.mean(axis=0), rtol=1e-10) and eng.get_state()[1][2] >= 2 and eng.get_state()[1][3] == 20
+    res["sharded_invariants"] = "ok" if all(gather(bool(ok))) else "VIOLATED"
+    res["sharded_resamplings"] = int(eng.get_state()[1][2])
+    eng.close()
+
+    comm = sb.api._distributed_setup("torch")
+    kw["resample"] = 2 * N
+    eng = sb.Engine(model, prior, device=local_rank, rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], flags=sb.SABC_FLAG_MG_STRICT_RESAMPLE, **kw)
+    eng.init()
+    th, u, r = eng.get_population()
+    all_th = np.concatenate(gather(th)); all_u = np.concatenate(gather(u))
+    eq = True
+    if rank == 0:
+        ref = sb.Engine(model, prior, device=local_rank, **kw); ref.init()
+        th1, u1, _ = ref.get_population()
+        key = lambda a: np.sort(np.ascontiguousarray(a).view([("", a.dtype)] * a.shape[1]).ravel())      # noqa: E731
+        eq = bool(np.array_equal(key(all_th), key(th1)) and np.array_equal(key(all_u), key(u1)) and np.array_equal(eng.get_state()[0], ref.get_state()[0]))
+        ref.close()
+    res["strict_resample_multiset_vs_1gpu"] = "equal" if all(gather(eq)) else "DIFFERENT"
+    eng.close()
+    return res
+
 def main():
     # stdout carries exactly one JSON line: everything libraries print there (e.g. NCCL's version banner) goes to stderr
     real_stdout = os.dup(1)
@@ -183,9 +289,11 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer (e2e) leg; default min(steps, 50)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` object (other configurations) and, on several GPUs, `mg_parity`")
     ap.add_argument("--ecdf-knots", type=int, default=0, help="compressed ECDF mode: keep K quantiles (0 = the reference's full ECDF)")
     ap.add_argument("--flags", type=int, default=0, help="extra SABC_FLAG_* bits for the engine (tuning)")
     ap.add_argument("--graph", action="store_true", help="replay the CUDA graph in the timed region (kernel times then come from a separate pass)")
+    ap.add_argument("--single-process", action="store_true", help="with --gpus N and no torchrun: ONE process drives the N GPUs through one handle (sabc_config.n_gpus)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -197,17 +305,28 @@ def main():
     model, prior, algorithm, n_default, desc = workload(args.workload)
     n_per_gpu = args.particles or n_default
     d, s = model.n_para, model.n_stats
+    n_group = args.gpus if (args.single_process and world == 1 and args.gpus > 1) else 0     # GPUs behind ONE handle
+    n_gpus_total = max(world, n_group, 1)
+    N = n_per_gpu * n_gpus_total
+
+    def config(**more):
+        c = {"workload": desc, "particles_per_gpu": n_per_gpu, "n_particles": N, "n_para": d, "n_stats": s, "algorithm": algorithm,
+             "proposal": "DifferentialEvolution", "resample": 2 * N, "checkpoint_history": 1, "ecdf_max_knots": args.ecdf_knots,
+             "rng": "Philox4x32-10 counter streams"}
+        c.update(more)
+        return c
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
+        N = n_per_gpu * max(world, args.gpus)
         val, cores, sample, ms = cpu_oracle_throughput(model, prior, algorithm, target_seconds=float(os.environ.get("SABC_BENCH_REF_SECONDS", "60")), steps=args.steps,
-                                                       warmup=args.warmup, max_particles=n_per_gpu * max(world, args.gpus))
+                                                       warmup=args.warmup, max_particles=N)
         line = {"impl": "reference", "metric": "particle-sim-updates/sec", "value": val, "unit": "particle-updates/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "particles_per_gpu": n_per_gpu, "proposal": "DifferentialEvolution"},
+                "config": config(),
                 "cpu_baseline": {"value": val, "unit": "particle-updates/s", "cores": cores, "kind": "port", "sample": sample,
                                  "note": "C/OpenMP restatement of the reference (oracle/), not the Julia package: julia is not installed"},
                 "e2e": {"value": val, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -236,22 +355,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    N = n_per_gpu * world
-    time_kernels_live = not args.graph and world == 1
+    time_kernels_live = not args.graph and world == 1 and n_group == 0
     flags = (sb.SABC_FLAG_TIME_KERNELS if time_kernels_live else 0) | args.flags
     kw = dict(n_particles=N, algorithm=algorithm, proposal=sb.DifferentialEvolution(n_para=d), resample=2 * N, v=1.0, delta=0.1,
               device=local_rank)
     comm = sb.api._distributed_setup("torch") if world > 1 else (0, 1, None)
     kw["ecdf_max_knots"] = args.ecdf_knots
-    eng = sb.Engine(model, prior, rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], flags=flags, **kw)
+    eng = sb.Engine(model, prior, rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], flags=flags, n_gpus=n_group, **kw)
     eng.init()
 
     # device-resident throughput ("value")
@@ -264,45 +374,34 @@ def main():
     eng.update(args.steps * N)             # blocking; timed inside with CUDA events on the engine's stream
     barrier()
     t = eng.timing()
-    if rank == 0:
-        sampler.stop()
     cnt1 = eng.get_state()[1]
     ms_total = max_over_ranks(t["update_ms"])
     value = args.steps * N / (ms_total * 1e-3)
     accept_frac = float(cnt1[1] - cnt0[1]) / float(args.steps * N)
 
-    # kernel time of the dominant kernel (update_half): live in the timed region, or from a separate pass when the graph is replayed
+    # kernel time of the dominant kernel: live in the timed region, or from a separate pass when the graph is replayed
     if time_kernels_live:
-        kernel_ms, kernel_launches, how = t["kernel_ms"], t["kernel_launches"], "CUDA events around every update_half launch inside the timed region"
+        kernel_ms, kernel_launches, how = t["kernel_ms"], t["kernel_launches"], "CUDA events around every launch of the dominant kernel inside the timed region"
+        share = kernel_ms / t["update_ms"]
     else:
         e2 = sb.Engine(model, prior, rank=0, world_size=1, flags=sb.SABC_FLAG_TIME_KERNELS, **{**kw, "n_particles": n_per_gpu, "resample": 2 * n_per_gpu})
         e2.init(); e2.update(args.warmup * n_per_gpu); e2.update(args.steps * n_per_gpu)
         t2 = e2.timing()
-        kernel_ms, kernel_launches, how = t2["kernel_ms"], t2["kernel_launches"], "separate pass of the same steps with CUDA events around every update_half launch (1 GPU slice)"
+        kernel_ms, kernel_launches, how = t2["kernel_ms"], t2["kernel_launches"], "separate pass of the same steps with CUDA events around every launch of the dominant kernel (one GPU's slice)"
+        share = t2["kernel_ms"] / t2["update_ms"]
         e2.close()
     kinfo = eng.kernel_info()
     bytes_per_update = algorithmic_bytes_per_update(d, s, accept_frac)
     avg_kernel_ms = kernel_ms / max(kernel_launches, 1)
     bytes_per_launch = bytes_per_update * (n_per_gpu / 2)
-    achieved = bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
+    hbm_achieved = bytes_per_launch / (avg_kernel_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_hbm()
-    traffic = None                         # DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    pipes = None                           # and its pipe utilisation from the same capture (what actually bounds a non-HBM kernel)
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        key = None
-        if model.name == "sir_tauleap" and n_per_gpu == 1_250_000:
-            key = "simulate_accept_kernel<sir_tauleap>"
-        elif model.name == "gauss_mean" and n_per_gpu == 10_000_000:
-            key = "update_half_kernel<gauss_mean, DE>@5000000"
-        if key:
-            traffic = tr.get(key)
-            pipes = tr.get("pipes", {}).get(key)
-    except Exception:
-        pass
+    heavy = model.name in ("sir_tauleap", "logistic") or model.name.startswith("sir_gillespie")
+    kname = (f"simulate_accept_kernel<{model.name}>" if heavy else f"update_half_kernel<{model.name}, DE>")
+    counts, counts_src = ncu_counts(f"{kname}@{n_per_gpu // 2}")
 
     # end-to-end through the host-buffer call (what Julia's update_population!(::SABCresult) would ccall): every step uploads
-    # the slice (θ,u,ρ,ε,counters) from pinned memory, runs one population update and downloads the result
+    # the population (theta,u,rho,eps,counters) from pinned memory, runs one population update and downloads the result
     e2e_steps = args.e2e_steps or min(args.steps, 50)
     import ctypes as C
     nl = eng.n_local
@@ -325,42 +424,83 @@ def main():
         tt = eng.timing()
         e2e_ms += tt["host_ms"]
     barrier()
+    if rank == 0:
+        sampler.stop()
     e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = e2e_steps * N / (e2e_ms * 1e-3)
     io_bytes = 8 * nl * (d + 2 * s) + 8 * eng.n_eps + 32
     for b in bufs:
         sb._lib.lib().sabc_host_free(b.ctypes.data_as(C.c_void_p))
+    eng.close()
+
+    parity = None
+    if world > 1 and not args.no_extra:
+        parity = mg_parity(sb, dist, rank, world, local_rank)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
+    clocks = sampler.summary()
+    launch = ("direct launches with event pairs" if time_kernels_live else
+              ("CUDA graph replay (one all-gather per update inside the graph), host looks " + "4 updates ahead" if world > 1 or n_group else "CUDA graph replay"))
+    if (args.flags & sb.SABC_FLAG_NO_GRAPH) and not time_kernels_live:
+        launch = "direct launches"
+    roof = {"kernel": kname + (" (split path: propose -> compacted simulate+accept -> stats)" if heavy else ""),
+            "avg_kernel_ms": avg_kernel_ms, "kernel_launches": int(kernel_launches), "kernel_share_of_step": share,
+            "updates_per_launch": n_per_gpu / 2, "grid": kinfo, "timing": how,
+            "hbm": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_update": bytes_per_update},
+            "traffic": counts["dram_bytes_per_launch"] if counts else None,
+            "ncu": counts if counts else None, "ncu_source": counts_src}
+    if heavy:
+        # this kernel is bound by instruction issue and divergence, not by HBM: achieved = warp instructions
+        # per second (count per launch from the committed ncu capture of this very kernel build, time measured live), peak = one
+        # warp instruction per scheduler and cycle at the SM clock sampled under load
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        peak_issue = 148 * 4 * sm_mhz * 1e6 / 1e9
+        if counts:
+            ach = counts["warp_inst_per_launch"] / (avg_kernel_ms * 1e-3) / 1e9
+            roof.update({"bound": "issue", "achieved": ach, "peak": peak_issue, "unit": "Gwarp-inst/s", "frac": ach / peak_issue,
+                         "lane_efficiency": counts["thread_inst_per_launch"] / counts["warp_inst_per_launch"] / 32.0,
+                         "note": "instruction issue x divergence bound (frac = issue-slot utilisation; useful-lane share in lane_efficiency); the HBM figures are in `hbm`"})
+        else:
+            roof.update({"bound": "issue", "achieved": None, "peak": peak_issue, "unit": "Gwarp-inst/s", "frac": None,
+                         "note": "instruction issue x divergence bound; no current ncu instruction count (" + str(counts_src) + "); the HBM figures are in `hbm`"})
+    else:
+        roof.update({"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+                     "note": "state streaming + scattered ECDF / partner sectors; the kernel itself is held by L1 data-pipe wavefronts (DESIGN.md section 4)"})
     line = {
-        "metric": "particle-sim-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps,
+        "metric": "particle-sim-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": n_gpus_total, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "particles_per_gpu": n_per_gpu, "n_particles": N, "n_para": d, "n_stats": s, "algorithm": algorithm,
-                   "proposal": "DifferentialEvolution", "resample": 2 * N, "checkpoint_history": 1, "ecdf_max_knots": args.ecdf_knots,
-                   "rng": "Philox4x32-10 counter streams", "accept_fraction": accept_frac,
-                   "l2": f"per-GPU working set {(8 * nl * (d + 2 * s + 1) + 8 * s * (N + 2)) / 1e6:.0f} MB (state + ECDF tables) vs 126 MB L2; no explicit flush",
-                   "host_numa": numa,
-                   "launch": "direct launches with event pairs" if time_kernels_live else ("host-driven + NCCL" if world > 1 else "CUDA graph replay")},
+        "config": config(),
+        "run": {"accept_fraction": accept_frac, "host_numa": numa, "launch": launch, "processes": ("one per GPU (torchrun)" if world > 1 else "one"),
+                "gpus_per_handle": max(n_group, 1),
+                "l2": f"per-GPU working set {(8 * n_per_gpu * (d + 2 * s + 1) + 2 * 8 * s * (N + 2)) / 1e6:.0f} MB (state + ECDF tables and index) vs 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "how": "sabc_update_host per step: pinned host (theta,u,rho,eps,counters) -> device, one population update, device -> host; "
                        "CUDA events from the first uploaded byte to the last downloaded byte, transfers pipelined with the half-sweeps"},
         "gpu_launches": int(t["total_launches"]),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": (f"simulate_accept_kernel<{model.name}> (split path: propose -> compacted simulate+accept -> stats)"
-                                if model.name in ("sir_tauleap", "logistic") else f"update_half_kernel<{model.name}, DE>"), "avg_kernel_ms": avg_kernel_ms, "kernel_launches": int(kernel_launches),
-                     "kernel_share_of_step": kernel_ms / t["update_ms"] if time_kernels_live else None,
-                     "algorithmic_bytes_per_update": bytes_per_update, "updates_per_launch": n_per_gpu / 2, "peak_source": peak_src,
-                     "grid": kinfo, "timing": how, "ncu_pipes": pipes,
-                     "note": ("simulation-heavy model: FP64/INT-issue and divergence bound, not HBM bound (DESIGN.md section 4); profiles/ holds the pipe utilisation"
-                              if model.name in ("sir_tauleap", "logistic") else "state streaming + ECDF leaf sectors (DESIGN.md section 4)")},
-        "clocks": sampler.summary(),
+        "roofline": roof,
+        "clocks": clocks,
     }
+    if parity is not None:
+        line["mg_parity"] = parity
+    if world == 1 and n_group == 0 and not args.no_extra:
+        # the other BASELINE.json configurations at their nominal sizes, device-resident, a second or two each
+        extra = {}
+        try:
+            extra["c4_full_1e7_one_gpu"] = run_config(sb, "c4", 10_000_000, 10, 3, local_rank)
+            extra["c5_1e7"] = run_config(sb, "c5", 10_000_000, 20, 3, local_rank)
+            extra["c3_1e6"] = run_config(sb, "c3", 1_000_000, 20, 3, local_rank)
+            extra["c2_1e5"] = run_config(sb, "c2", 100_000, 200, 3, local_rank)
+            extra["c1_1e3"] = run_config(sb, "c1", 1000, 99, 3, local_rank)
+        except Exception as ex:                                          # never lose the main line
+            extra["error"] = f"{type(ex).__name__}: {ex}"
+        line["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
         val, cores, sample, _ = cpu_oracle_throughput(model, prior, algorithm, target_seconds=15.0, steps=3, warmup=1, max_particles=n_per_gpu, fixed_steps=False)
         line["cpu_baseline"] = {"value": val, "unit": "particle-updates/s", "cores": cores, "kind": "port", "sample": sample,

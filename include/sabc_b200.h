@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SABC_ABI_VERSION 2   /* 2: sabc_config ends with n_gpus, gpu_ids; sabc_timing ends with d2h_bytes */
+#define SABC_ABI_VERSION 2   /* 2: sabc_config ends with n_gpus, gpu_ids */
 
 /* error classes; the first block mirrors the reference's error() sites */
 #define SABC_OK                 0
@@ -106,7 +106,6 @@ typedef struct sabc_timing {
     double  host_ms;           /* host-buffer call: first byte up to last byte down, CUDA events */
     double  resample_ms;       /* multi-GPU: host wall time inside the global resampling exchanges */
     int64_t resample_events;
-    int64_t d2h_bytes;         /* host-buffer call: bytes of the result download (only the rows that changed unless a resampling fell into the call) */
 } sabc_timing;
 
 /* ---- lifetime ---- */

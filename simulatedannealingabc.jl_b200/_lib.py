@@ -52,7 +52,7 @@ class Config(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("update_ms", C.c_double), ("kernel_ms", C.c_double), ("kernel_launches", C.c_int64),
                 ("total_launches", C.c_int64), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("host_ms", C.c_double),
-                ("resample_ms", C.c_double), ("resample_events", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("resample_ms", C.c_double), ("resample_events", C.c_int64)]
 
 
 # every symbol include/sabc_b200.h declares: name -> (restype, argtypes)

@@ -22,7 +22,9 @@ from .models import DeviceModel
 from .proposals import DifferentialEvolution, Proposal, RandomWalk, StretchMove  # noqa: F401
 
 ALGORITHMS = {"single_eps": 0, "multi_eps": 1}
-# north_star vocabulary: type=:single|:multi|:hybrid  
+# north_star vocabulary: type=:single|:multi|:hybrid  (SURVEY.md §0).  The reference (v0.4.0) has algorithm = :single_eps | :multi_eps
+# only; "hybrid" is its :single_eps applied to several statistics (one eps, per-statistic ECDFs, sum_j du_j / eps,
+# src/SimulatedAnnealingABC.jl:318-319, table :439-446) -- state.algorithm therefore reports single_eps for it.
 TYPES = {"single": "single_eps", "multi": "multi_eps", "hybrid": "single_eps"}
 
 
@@ -196,11 +198,9 @@ class SABCresult:
     def _fetch(self):
         if self._cache is None:
             self._cache = list(self._engine.get_population())
+            for a in self._cache:
+                a.flags.writeable = False      # an in-place edit would never reach the device: assign a whole array to the field instead
         return self._cache
-
-    def _invalidate(self):
-        if not self._dirty:
-            self._cache = None
 
     @property
     def population(self):

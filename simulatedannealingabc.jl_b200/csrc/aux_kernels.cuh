@@ -145,7 +145,7 @@ SABC_D void d_post1_block(const Post1Args& a, int b, double* s_w) {
 }
 static __global__ void __launch_bounds__(CHUNK) k_post1(const Post1Args a) {
     __shared__ double s_w[8];
-    if (a.ds->hold) return;
+    if (halted(a.ds)) return;
     d_post1_block(a, blockIdx.x, s_w);
 }
 static __global__ void k_decide(DevState* ds, int S, int64_t n_global, int64_t resample) {
@@ -259,7 +259,13 @@ static __global__ void __launch_bounds__(1024) k_scan_tiles(const unsigned long 
         if (threadIdx.x == 1023) s_carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total_out = s_carry;
+    if (threadIdx.x == 0) {
+        *total_out = s_carry;
+        // every 32.32 fixed-point weight flushed to zero (delta u / mean u beyond ~22 for all particles): fail like the sharded
+        // path does instead of collapsing the population onto one particle
+        // (force == 2: a rank of a sharded population, whose slice alone may legitimately weigh nothing)
+        if (s_carry == 0ull && total_out == &ds->w_total && force != 2) atomicOr(const_cast<int*>(&ds->error_flag), 4);
+    }
 }
 // inclusive prefix sums in place: q[i] <- tile_off + Σ_{k<=i in tile} q[k]
 SABC_D void d_prefix(unsigned long long* q, int64_t n, const unsigned long long* tile_off, int vb, int vg, unsigned long long* s_warp) {
@@ -340,7 +346,7 @@ SABC_D void d_draw_gather(const PopView& pop, const PopView& tmp, int64_t n, int
 }
 static __global__ void __launch_bounds__(CHUNK) k_draw_gather(PopView pop, PopView tmp, int64_t n, int D, int S,
                                                        const unsigned long long* P, uint64_t seed, DevState* ds, int force) {
-    if (!force && !ds->resample_flag) return;
+    if ((!force && !ds->resample_flag) || ds->error_flag) return;
     __shared__ unsigned long long s_acc[2 * MAX_S];
     d_draw_gather(pop, tmp, n, D, S, P, seed, ds, blockIdx.x, gridDim.x, s_acc);
 }
@@ -352,7 +358,7 @@ SABC_D void d_copyback(const PopView& pop, const PopView& tmp, int64_t n, int D,
     }
 }
 static __global__ void k_copyback(PopView pop, PopView tmp, int64_t n, int D, int S, const DevState* ds, int force) {
-    if (!force && !ds->resample_flag) return;
+    if ((!force && !ds->resample_flag) || ds->error_flag) return;
     d_copyback(pop, tmp, n, D, S, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 // indices only (parity hook)
@@ -418,7 +424,7 @@ SABC_D void d_finish(const FinishArgs& a, double* s_um, unsigned long long* s_hi
 static __global__ void k_finish(const FinishArgs a) {
     __shared__ double s_um[MAX_S];
     __shared__ unsigned long long s_hi[MAX_S], s_lo[MAX_S];
-    if (a.ds->hold) return;
+    if (halted(a.ds)) return;
     d_finish(a, s_um, s_hi, s_lo);
 }
 
@@ -439,6 +445,7 @@ static __global__ void __launch_bounds__(CHUNK) k_tail_small(const TailArgs a) {
     DevState* ds = a.post.ds;
     for (int b = 0; b <= 2 * a.S; ++b) d_post1_block(a.post, b, s_w);
     __syncthreads();
+    if (halted(ds)) return;
     if (ds->resample_flag) {
         d_weights(a.pop, a.n, a.S, a.delta, ds, a.q, a.tile_sum, 0, 1, s8, s_ubar);
         __syncthreads();
@@ -447,10 +454,12 @@ static __global__ void __launch_bounds__(CHUNK) k_tail_small(const TailArgs a) {
             const int64_t n_tiles = (a.n + TILE - 1) / TILE;
             for (int64_t t = 0; t < n_tiles; ++t) { a.tile_off[t] = run; run += a.tile_sum[t]; }
             ds->w_total = run;
+            if (run == 0ull) atomicOr(&ds->error_flag, 4);
         }
         __syncthreads();
         d_prefix(a.q, a.n, a.tile_off, 0, 1, s8);
         __syncthreads();
+        if (ds->error_flag) return;                       // all weights zero (uniform across the CTA)
         d_draw_gather(a.pop, a.tmp, a.n, a.D, a.S, a.q, a.seed, ds, 0, 1, s_acc);
         __syncthreads();
         d_copyback(a.pop, a.tmp, a.n, a.D, a.S, threadIdx.x, blockDim.x);
@@ -477,11 +486,11 @@ static __global__ void __launch_bounds__(CHUNK) k_rw_cross_sums(const double* th
     }
 }
 static __global__ void k_rw_means(DevState* ds, const double* sums, int D, int64_t n_global) {
-    if (ds->hold) return;
+    if (halted(ds)) return;
     if (threadIdx.x < D) ds->mom[threadIdx.x] = sums[threadIdx.x] / (double)n_global;
 }
 static __global__ void k_rw_chol(DevState* ds, const double* sums, int D, int64_t n_global, double beta) {
-    if (threadIdx.x != 0 || ds->hold) return;
+    if (threadIdx.x != 0 || halted(ds)) return;
     double Sg[MAX_D * MAX_D];
     int p = 0;
     for (int a = 0; a < D; ++a) for (int b = 0; b <= a; ++b, ++p) {
@@ -501,7 +510,7 @@ static __global__ void k_rw_chol(DevState* ds, const double* sums, int D, int64_
 static __global__ void k_begin(DevState* ds, long long t, long long n_pop, long long checkpoint) {
     ds->t = t; ds->ix = 1; ds->n_pop = n_pop; ds->checkpoint = checkpoint; ds->rec = 0; ds->last_cp = 0;
     for (int j = 0; j < MAX_S; ++j) { ds->u_hi[j] = 0ull; ds->u_lo[j] = 0ull; }
-    ds->n_acc_iter = 0ull; ds->resample_flag = 0; ds->hold = 0;
+    ds->n_acc_iter = 0ull; ds->resample_flag = 0; ds->hold = 0; ds->error_flag = 0;    // an earlier call's error does not stick
     for (int k = 0; k < MAX_SLOTS; ++k) { ds->list_count[k] = 0u; ds->list_cursor[k] = 0u; }
 }
 // Σu limbs of an existing u array (set_population, multi-GPU resampling)

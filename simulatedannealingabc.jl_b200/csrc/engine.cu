@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -31,21 +32,28 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+// Entries have stable addresses (std::deque never moves an element on push_back): engines keep a pointer to their model's entry, and a
+// plug-in loaded later (dlopen of an out-of-tree model) must not invalidate it.  The name is copied: the caller's string may go away.
 static std::mutex g_reg_mutex;
-static std::vector<ModelVTable>& registry() { static std::vector<ModelVTable> r; return r; }
+static std::deque<ModelVTable>& registry() { static std::deque<ModelVTable> r; return r; }
+static std::deque<std::string>& registry_names() { static std::deque<std::string> r; return r; }
+static void registry_add(const ModelVTable& v) {
+    registry_names().emplace_back(v.name);
+    registry().push_back(v);
+    registry().back().name = registry_names().back().c_str();
+}
 static void ensure_builtin_models() {
     static std::once_flag once;
     std::call_once(once, [] {
-        auto& r = registry();
-        r.push_back(ModelLaunchers<GaussMean>::vtable("gauss_mean"));
-        r.push_back(ModelLaunchers<GaussSample<1, 1>>::vtable("gauss_sample_d1s1"));
-        r.push_back(ModelLaunchers<GaussSample<1, 2>>::vtable("gauss_sample_d1s2"));
-        r.push_back(ModelLaunchers<GaussSample<2, 1>>::vtable("gauss_sample_d2s1"));
-        r.push_back(ModelLaunchers<GaussSample<2, 2>>::vtable("gauss_sample_d2s2"));
-        r.push_back(ModelLaunchers<Logistic>::vtable("logistic", 1));
-        r.push_back(ModelLaunchers<SirTauLeap>::vtable("sir_tauleap", 1));
-        r.push_back(ModelLaunchers<SirGillespie<3>>::vtable("sir_gillespie_s3", 1));
-        r.push_back(ModelLaunchers<SirGillespie<1>>::vtable("sir_gillespie_s1", 1));
+        registry_add(ModelLaunchers<GaussMean>::vtable("gauss_mean"));
+        registry_add(ModelLaunchers<GaussSample<1, 1>>::vtable("gauss_sample_d1s1"));
+        registry_add(ModelLaunchers<GaussSample<1, 2>>::vtable("gauss_sample_d1s2"));
+        registry_add(ModelLaunchers<GaussSample<2, 1>>::vtable("gauss_sample_d2s1"));
+        registry_add(ModelLaunchers<GaussSample<2, 2>>::vtable("gauss_sample_d2s2"));
+        registry_add(ModelLaunchers<Logistic>::vtable("logistic", 1));
+        registry_add(ModelLaunchers<SirTauLeap>::vtable("sir_tauleap", 1));
+        registry_add(ModelLaunchers<SirGillespie<3>>::vtable("sir_gillespie_s3", 1));
+        registry_add(ModelLaunchers<SirGillespie<1>>::vtable("sir_gillespie_s1", 1));
     });
 }
 const ModelVTable* find_model(const char* name) {
@@ -114,9 +122,6 @@ struct sabc_engine {
     DevBuf<double> b_sp_theta, b_sp_lp, b_sp_lf;      // split path work list
     DevBuf<uint32_t> b_sp_idx, b_sp_key, b_sp_perm;
     DevBuf<unsigned int> b_sp_hist, b_sp_off;
-    DevBuf<unsigned char> b_dirty;                     // host-buffer calls: rows accepted since the last upload
-    DevBuf<double> b_pack; DevBuf<unsigned int> b_pack_cnt;
-    double* h_pack = nullptr; unsigned int* h_pack_cnt = nullptr; int64_t pack_cap = 0;   // pinned staging of the compact download
     bool sort_work = false;
     bool split = false;
     int grid_simacc = 0, bps_simacc = 0;
@@ -144,8 +149,6 @@ struct sabc_engine {
     sabc_timing timing{};
 
     ~sabc_engine() {
-        if (h_pack) cudaFreeHost(h_pack);
-        if (h_pack_cnt) cudaFreeHost(h_pack_cnt);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (auto* b : ecdf_bufs) delete b;
         comm.destroy();
@@ -428,6 +431,7 @@ static int sync_state_from_device(sabc_engine* e, int64_t* n_rec_out) {
     if (n_rec_out) *n_rec_out = h.rec;
     if (h.error_flag & 1) return set_error(SABC_ERR_NEG_DISTANCE, "Negative distances are not allowed!");
     if (h.error_flag & 2) return set_error(SABC_ERR_UBAR_ZERO, "Division by zero - Mean u for a statistic <= eps()");
+    if (h.error_flag & 4) return set_error(SABC_ERR_INVALID, "all resampling weights are zero: delta * u / mean(u) is beyond the range of the 32.32 fixed-point weights for every particle");
     return 0;
 }
 
@@ -515,14 +519,20 @@ int sabc_register_model(const void* vtable) {
     if (!vtable) return set_error(SABC_ERR_INVALID, "null vtable");
     ensure_builtin_models();
     const ModelVTable* vt = (const ModelVTable*)vtable;
+    if (vt->struct_size != (uint32_t)sizeof(ModelVTable) || vt->abi_version != SABC_MODEL_VTABLE_VERSION)
+        return set_error(SABC_ERR_INVALID, "model launch table was built against other kernel headers (size %u, version %u; this library: %u, %u)",
+                         vt->struct_size, vt->abi_version, (unsigned)sizeof(ModelVTable), (unsigned)SABC_MODEL_VTABLE_VERSION);
+    if (!vt->name || !vt->name[0]) return set_error(SABC_ERR_INVALID, "model launch table without a name");
     std::lock_guard<std::mutex> lk(g_reg_mutex);
-    for (auto& m : registry()) if (std::strcmp(m.name, vt->name) == 0) { m = *vt; return 0; }
-    registry().push_back(*vt);
+    for (auto& m : registry())
+        if (std::strcmp(m.name, vt->name) == 0) { const char* keep = m.name; m = *vt; m.name = keep; return 0; }   // same entry, same address
+    registry_add(*vt);
     return 0;
 }
-int sabc_model_count(void) { ensure_builtin_models(); return (int)registry().size(); }
+int sabc_model_count(void) { ensure_builtin_models(); std::lock_guard<std::mutex> lk(g_reg_mutex); return (int)registry().size(); }
 const char* sabc_model_name(int i) {
     ensure_builtin_models();
+    std::lock_guard<std::mutex> lk(g_reg_mutex);
     return (i >= 0 && i < (int)registry().size()) ? registry()[i].name : nullptr;
 }
 int sabc_model_info(const char* name, int32_t* n_para, int32_t* n_stats) {
@@ -619,7 +629,8 @@ int sabc_create(sabc_engine** out, const sabc_config* c) {
     A(e->b_tile_sum.alloc((size_t)n_tiles)); A(e->b_tile_off.alloc((size_t)n_tiles));
     e->part_ld = ((int64_t)n + CHUNK - 1) / CHUNK + 1;
     A(e->b_rho_part.alloc((size_t)2 * e->S * e->part_ld));
-    e->scratch_ld = e->part_ld / CHUNK + 8;
+    e->scratch_ld = 8;                                   // cta_treesum writes every level's partials: ceil(g/256) + ceil(.../256) + ...
+    for (int64_t g = (e->part_ld + CHUNK - 1) / CHUNK; ; g = (g + CHUNK - 1) / CHUNK) { e->scratch_ld += g; if (g <= 1) break; }
     const int ncol = std::max(2 * e->S + 1, e->D * (e->D + 1) / 2 + e->D);
     A(e->b_scratch.alloc((size_t)ncol * e->scratch_ld));
     A(e->b_rw_part.alloc((size_t)(e->D * (e->D + 1) / 2) * e->part_ld * 2)); A(e->b_rw_sums.alloc(MAX_D * MAX_D));
@@ -674,9 +685,14 @@ int sabc_set_tuning(sabc_engine* e, double v, double delta, int64_t resample, in
     if (proposal == SABC_PROP_RW && !(prop_par[0] > 0.0 && prop_par[0] <= 1.0))
         return set_error(SABC_ERR_BAD_PROPOSAL, "Mixing parameter `β` must be between zero and one.");
     if (resample <= 0) return set_error(SABC_ERR_INVALID, "resample must be positive");
+    const bool same = e->v == v && e->delta == delta && e->resample == resample && e->proposal == proposal &&
+                      e->prop_par[0] == prop_par[0] && e->prop_par[1] == prop_par[1];
+    if (same) return 0;                                       // nothing to re-capture: update_population! passes its keywords on every call
+    const bool new_kernel = e->proposal != proposal;
     e->v = v; e->delta = delta; e->resample = resample;       // v, δ are validated by sabc_update like the reference (:261-262)
     e->proposal = proposal; e->prop_par[0] = prop_par[0]; e->prop_par[1] = prop_par[1];
-    if (e->top_doubles > 0) SABC_TRY(ecdf_finalize(e));       // occupancy / grid of the newly selected kernel; drops the graph
+    if (e->top_doubles > 0 && new_kernel) SABC_TRY(ecdf_finalize(e));       // occupancy / grid of the newly selected kernel
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // the captured arguments hold the old values
     return 0;
 }
 
@@ -775,9 +791,13 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
     SABC_CUDA(cudaGetLastError());
     if (e->sharded()) SABC_TRY(launch_update_proposal_mg(e)); else SABC_TRY(launch_update_proposal(e));   // :284
 
-    cudaEvent_t ev0, ev1;
-    SABC_CUDA(cudaEventCreate(&ev0)); SABC_CUDA(cudaEventCreate(&ev1));
     std::vector<cudaEvent_t> kev;
+    struct EventGuard {                                   // every exit path below, early error returns included, destroys the events
+        cudaEvent_t a = nullptr, b = nullptr; std::vector<cudaEvent_t>* k;
+        ~EventGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); for (auto ev : *k) cudaEventDestroy(ev); }
+    } guard{nullptr, nullptr, &kev};
+    SABC_CUDA(cudaEventCreate(&guard.a)); SABC_CUDA(cudaEventCreate(&guard.b));
+    const cudaEvent_t ev0 = guard.a, ev1 = guard.b;
     const bool time_kernels = (e->flags & SABC_FLAG_TIME_KERNELS) != 0;
     int rc = 0;
     const bool piped = (bool)e->pipe_before || (bool)e->pipe_after;
@@ -871,9 +891,7 @@ int sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history
     e->timing.total_launches = ((int64_t)kernels_per_iteration(e) + (int64_t)(e->split ? 4 : 2) * (e->pipe_nsub - 1)) * n_pop;
     for (size_t k = 0; k + 1 < kev.size(); k += 2) {
         float t = 0.f; cudaEventElapsedTime(&t, kev[k], kev[k + 1]); e->timing.kernel_ms += t;
-        cudaEventDestroy(kev[k]); cudaEventDestroy(kev[k + 1]);
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (rc) return rc;
     SABC_TRY(append_history(e, n_rec));
     e->n_simulation += n_pop * e->N;                                 // :391
@@ -941,82 +959,13 @@ int sabc_set_population(sabc_engine* e, const double* theta, const double* u, co
     return set_population_ld(e, theta, u, rho, e->n_local, eps, counters);
 }
 
-// Rows whose particle accepted during a host-buffer call, packed as [row index, theta.., u.., rho..] for a compact download:
-// one population update changes only the accepted rows (about a(1 - prior rejects) of them), so shipping all three matrices
-// home again would move several times the bytes that changed.
-static __global__ void __launch_bounds__(CHUNK) k_compact_dirty(PopView pop, int64_t n, int D, int S, double* pack, unsigned int cap,
-                                                         unsigned int* count) {
-    const int lane = threadIdx.x & 31, w = 1 + D + 2 * S;
-    const int64_t n_round = (n + 31) / 32 * 32;
-    for (int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * CHUNK) {
-        const bool d = i < n && pop.dirty[i] != 0;
-        const unsigned mask = __ballot_sync(0xffffffffu, d);
-        unsigned base = 0;
-        if (lane == 0 && mask) base = atomicAdd(count, (unsigned)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (d) {
-            const unsigned pos = base + __popc(mask & ((1u << lane) - 1u));
-            if (pos < cap) {
-                double* row = pack + (size_t)pos * w;
-                row[0] = (double)i;
-                for (int c = 0; c < D; ++c) row[1 + c] = pop.theta[c * pop.ld + i];
-                for (int j = 0; j < S; ++j) { row[1 + D + j] = pop.u[j * pop.ld + i]; row[1 + D + S + j] = pop.rho[j * pop.ld + i]; }
-            }
-        }
-    }
-}
-
-// bring the result of a host-buffer call home: only the rows that changed when no resampling fell into the call (and the
-// packed rows fit the staging buffer), everything otherwise
-static int download_result(sabc_engine* e, double* theta, double* u, double* rho, int64_t ld, bool resampled) {
-    const int64_t n = e->n_local;
-    const int w = 1 + e->D + 2 * e->S;
-    e->timing.d2h_bytes = 0;
-    if (!resampled && e->pop.dirty && e->pack_cap > 0) {
-        SABC_CUDA(cudaMemsetAsync(e->b_pack_cnt.p, 0, sizeof(unsigned int), e->s_out));
-        const int grid = (int)std::min<int64_t>((n + CHUNK - 1) / CHUNK, (int64_t)e->n_sm * 8);
-        k_compact_dirty<<<grid, CHUNK, 0, e->s_out>>>(e->pop, n, e->D, e->S, e->b_pack.p, (unsigned)e->pack_cap, e->b_pack_cnt.p);
-        SABC_CUDA(cudaGetLastError());
-        unsigned int cnt = 0;
-        SABC_CUDA(cudaMemcpyAsync(&e->h_pack_cnt[0], e->b_pack_cnt.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->s_out));
-        SABC_CUDA(cudaStreamSynchronize(e->s_out));
-        cnt = e->h_pack_cnt[0];
-        if ((int64_t)cnt <= e->pack_cap) {
-            if (cnt > 0) {
-                SABC_CUDA(cudaMemcpyAsync(e->h_pack, e->b_pack.p, (size_t)cnt * w * sizeof(double), cudaMemcpyDeviceToHost, e->s_out));
-                SABC_CUDA(cudaStreamSynchronize(e->s_out));
-                // scatter on the host, a few threads: the rows are disjoint
-                const int D = e->D, S = e->S;
-                const double* pk = e->h_pack;
-                auto work = [=](unsigned lo, unsigned hi) {
-                    for (unsigned k = lo; k < hi; ++k) {
-                        const double* row = pk + (size_t)k * w;
-                        const int64_t i = (int64_t)row[0];
-                        for (int c = 0; c < D; ++c) theta[c * ld + i] = row[1 + c];
-                        for (int j = 0; j < S; ++j) { u[j * ld + i] = row[1 + D + j]; rho[j * ld + i] = row[1 + D + S + j]; }
-                    }
-                };
-                const unsigned nt = cnt < 20000u ? 1u : 4u;
-                std::vector<std::thread> th;
-                for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, (unsigned)((uint64_t)cnt * t / nt), (unsigned)((uint64_t)cnt * (t + 1) / nt));
-                work(0, (unsigned)((uint64_t)cnt / nt));
-                for (auto& t : th) t.join();
-            }
-            e->timing.d2h_bytes = (int64_t)cnt * w * (int64_t)sizeof(double) + 4;
-            return 0;
-        }
-    }
-    SABC_TRY(copy_rows(theta, ld, e->pop.theta, n, e->D, 0, n, cudaMemcpyDeviceToHost, e->s_out));
-    SABC_TRY(copy_rows(u, ld, e->pop.u, n, e->S, 0, n, cudaMemcpyDeviceToHost, e->s_out));
-    SABC_TRY(copy_rows(rho, ld, e->pop.rho, n, e->S, 0, n, cudaMemcpyDeviceToHost, e->s_out));
-    SABC_CUDA(cudaStreamSynchronize(e->s_out));
-    e->timing.d2h_bytes = (int64_t)n * (e->D + 2 * e->S) * (int64_t)sizeof(double);
-    return 0;
-}
-
-// update_population!(::SABCresult) with the result held in host buffers (leading dimension ld).  The upload is issued in order
-// of need and pipelined with the half-sweeps: the first sweep starts as soon as theta of the second half (its partners) and the
-// first sub-range of the first half have arrived, the rest of the upload overlaps it.  Only the rows that changed travel home.
+// update_population!(::SABCresult) with the result held in host buffers (leading dimension ld).  For large slices the transfers
+// are pipelined with the two half-sweeps: the upload is issued in order of need, the first sweep starts as soon as theta of the
+// second half (its partners) and the first sub-range of the first half have arrived, and every sub-range goes home as soon as
+// its last sweep is done while the next one is simulated.
+// (Measured and rejected in round 2: downloading only the rows that accepted, packed on the device and scattered by host
+// threads -- 14-30 % of the rows change per update, nearly every cache line of the host arrays is touched, and the CPU
+// scatter is slower than the DMA of the whole matrices: 4.56 ms per C4 step against 3.5; profiles/r2_notes.md.)
 static int update_host_ld(sabc_engine* e, double* theta, double* u, double* rho, int64_t ld, double* eps, int64_t counters[4],
                           int64_t n_simulation, int64_t checkpoint_history) {
     if (!theta || !u || !rho || !eps || !counters) return set_error(SABC_ERR_INVALID, "null argument");
@@ -1024,68 +973,39 @@ static int update_host_ld(sabc_engine* e, double* theta, double* u, double* rho,
     const int64_t n = e->n_local, h0 = n / 2, n_pop = n_simulation / e->N;
     const bool pipe = n_pop >= 1 && n >= 32768 && !(e->flags & SABC_FLAG_NO_PIPELINE) && !e->replicated && e->top_doubles > 0 &&
                       e->v > 0.0 && e->delta > 0.0;
-    if (!e->s_in) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
-    if (!e->s_out) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-    // dirty-row tracking and the staging buffers of the compact download (first host call)
-    const bool compact = !(e->flags & SABC_FLAG_NO_PIPELINE) && !e->replicated;
-    if (compact && !e->b_dirty.p) {
-        const int w = 1 + e->D + 2 * e->S;
-        e->pack_cap = n / 2 + 1024;
-        SABC_CUDA(e->b_dirty.alloc((size_t)n)); SABC_CUDA(e->b_pack.alloc((size_t)e->pack_cap * w)); SABC_CUDA(e->b_pack_cnt.alloc(1));
-        SABC_CUDA(cudaHostAlloc((void**)&e->h_pack, (size_t)e->pack_cap * w * sizeof(double), cudaHostAllocDefault));
-        SABC_CUDA(cudaHostAlloc((void**)&e->h_pack_cnt, sizeof(unsigned int) * 4, cudaHostAllocDefault));
-    }
     cudaEvent_t a, b, c, d;
     SABC_CUDA(cudaEventCreate(&a)); SABC_CUDA(cudaEventCreate(&b)); SABC_CUDA(cudaEventCreate(&c)); SABC_CUDA(cudaEventCreate(&d));
     std::vector<cudaEvent_t> evs;
     auto cleanup = [&] { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); for (auto ev : evs) cudaEventDestroy(ev); };
-    auto finish_call = [&](int rc, const sabc_timing& t_upd, int64_t n_res_before) -> int {
+    int rc = 0;
+    if (!pipe) {
+        SABC_CUDA(cudaEventRecord(a, e->stream));
+        rc = set_population_ld(e, theta, u, rho, ld, eps, counters);
+        if (!rc) { SABC_CUDA(cudaEventRecord(b, e->stream)); rc = sabc_update(e, n_simulation, checkpoint_history); }
+        if (!rc) { SABC_CUDA(cudaEventRecord(c, e->stream)); rc = get_population_ld(e, theta, u, rho, ld); }
+        if (!rc) rc = sabc_get_state(e, eps, counters);
         if (!rc) {
-            SABC_CUDA(cudaEventRecord(c, e->s_out));
-            rc = download_result(e, theta, u, rho, ld, e->n_resampling != n_res_before);
-            if (!rc) rc = sabc_get_state(e, eps, counters);
-        }
-        if (!rc) {
-            SABC_CUDA(cudaEventRecord(d, e->s_out));
+            SABC_CUDA(cudaEventRecord(d, e->stream));
             SABC_CUDA(cudaEventSynchronize(d));
-            SABC_CUDA(cudaStreamSynchronize(e->s_in));
             float t1 = 0, t2 = 0, t3 = 0;
             cudaEventElapsedTime(&t1, a, b); cudaEventElapsedTime(&t2, c, d); cudaEventElapsedTime(&t3, a, d);
-            const int64_t d2h = e->timing.d2h_bytes;
-            e->timing = t_upd;
-            e->timing.h2d_ms = t1; e->timing.d2h_ms = t2; e->timing.host_ms = t3; e->timing.d2h_bytes = d2h;
-        } else {
-            cudaStreamSynchronize(e->s_in); cudaStreamSynchronize(e->s_out);
+            e->timing.h2d_ms = t1; e->timing.d2h_ms = t2; e->timing.host_ms = t3;
         }
         cleanup();
         return rc;
-    };
-    int rc = 0;
-    if (compact) {       // from the first host call on every accept marks its row (one byte); the flags are cleared per call
-        SABC_CUDA(cudaMemsetAsync(e->b_dirty.p, 0, (size_t)n, e->stream));
-        if (!e->pop.dirty) {
-            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }   // captured without the pointer
-            e->pop.dirty = e->b_dirty.p;
-        }
     }
-    if (!pipe) {
-        SABC_CUDA(cudaEventRecord(a, e->s_in));
-        SABC_CUDA(cudaStreamWaitEvent(e->stream, a, 0));
-        rc = set_population_ld(e, theta, u, rho, ld, eps, counters);
-        const int64_t n_res_before = e->n_resampling;
-        SABC_CUDA(cudaEventRecord(b, e->stream));
-        if (!rc) rc = sabc_update(e, n_simulation, checkpoint_history);
-        return finish_call(rc, e->timing, n_res_before);
-    }
+    if (!e->s_in) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    if (!e->s_out) SABC_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
     // 2 sub-ranges per half measured best on B200 (4.70 ms vs 4.85 at 1, 5.9 at 3, 6.8 at 4 per C4 step): the simulation
     // kernel needs ~150 k items to fill the GPU, smaller sub-sweeps only add latency-bound tails.  SABC_PIPE_NSUB overrides.
     const int nsub_env = getenv("SABC_PIPE_NSUB") ? atoi(getenv("SABC_PIPE_NSUB")) : 2;
     const int nsub = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nsub_env, (int)MAX_SUB), h0 / 32768));
-    cudaEvent_t evT1, evUp[2][MAX_SUB];
+    cudaEvent_t evT1, evUp[2][MAX_SUB], evDn[2][MAX_SUB];
     auto mk = [&](cudaEvent_t& ev) { cudaError_t r = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); if (r == cudaSuccess) evs.push_back(ev); return r; };
-    if (mk(evT1) != cudaSuccess) { cleanup(); return set_error(SABC_ERR_CUDA, "event creation failed"); }
-    for (int h = 0; h < 2; ++h) for (int j = 0; j < nsub; ++j) if (mk(evUp[h][j]) != cudaSuccess) { cleanup(); return set_error(SABC_ERR_CUDA, "event creation failed"); }
-    const auto H2D = cudaMemcpyHostToDevice;
+    bool ev_ok = mk(evT1) == cudaSuccess;
+    for (int h = 0; h < 2; ++h) for (int j = 0; j < nsub; ++j) ev_ok = ev_ok && mk(evUp[h][j]) == cudaSuccess && mk(evDn[h][j]) == cudaSuccess;
+    if (!ev_ok) { cleanup(); return set_error(SABC_ERR_CUDA, "event creation failed"); }
+    const auto H2D = cudaMemcpyHostToDevice; const auto D2H = cudaMemcpyDeviceToHost;
     auto rows = [&](int half, int sub, int64_t& r0, int64_t& r1) {       // absolute row range of a sub-range
         int64_t off, an, t0, t1;
         halves(e, half, off, an, t0, t1);
@@ -1110,7 +1030,8 @@ static int update_host_ld(sabc_engine* e, double* theta, double* u, double* rho,
     // state scalars; cached log-prior of the second half as soon as its theta is there
     SABC_CUDA(cudaStreamWaitEvent(e->stream, evT1, 0));
     k_recompute_lp<<<e->grid_aux, 256, 0, e->stream>>>(e->pop, h0, n, e->D, e->prior);
-    SABC_TRY(set_state_scalars(e, eps, counters));
+    rc = set_state_scalars(e, eps, counters);
+    if (rc) { cudaStreamSynchronize(e->s_in); cleanup(); return rc; }
     if (e->proposal == PROP_RW)        // update_proposal! (:284) reads the whole population before the first sweep
         SABC_CUDA(cudaStreamWaitEvent(e->stream, evUp[1][nsub - 1], 0));
     e->initialised = true;
@@ -1124,9 +1045,40 @@ static int update_host_ld(sabc_engine* e, double* theta, double* u, double* rho,
         }
         return 0;
     };
+    // after its (sub-)sweep of the last update a row range is final (unless a resampling follows): it goes home while
+    // the next sub-ranges are being simulated
+    e->pipe_after = [&](int half, int sub) -> int {
+        int64_t r0, r1; rows(half, sub, r0, r1);
+        SABC_CUDA(cudaEventRecord(evDn[half][sub], e->stream));
+        SABC_CUDA(cudaStreamWaitEvent(e->s_out, evDn[half][sub], 0));
+        SABC_TRY(copy_rows(theta, ld, e->pop.theta, n, e->D, r0, r1, D2H, e->s_out));
+        SABC_TRY(copy_rows(u, ld, e->pop.u, n, e->S, r0, r1, D2H, e->s_out));
+        return copy_rows(rho, ld, e->pop.rho, n, e->S, r0, r1, D2H, e->s_out);
+    };
     rc = sabc_update(e, n_simulation, checkpoint_history);          // blocks until the updates are done
-    e->pipe_before = nullptr; e->pipe_nsub = 1;
-    return finish_call(rc, e->timing, n_res_before);
+    e->pipe_before = nullptr; e->pipe_after = nullptr; e->pipe_nsub = 1;
+    const sabc_timing t_upd = e->timing;
+    if (!rc) {
+        SABC_CUDA(cudaEventRecord(c, e->s_out));
+        if (e->n_resampling != n_res_before) {                      // theta, u of every row changed after the sweeps
+            rc = copy_rows(theta, ld, e->pop.theta, n, e->D, 0, n, D2H, e->s_out);
+            if (!rc) rc = copy_rows(u, ld, e->pop.u, n, e->S, 0, n, D2H, e->s_out);
+        }
+        if (!rc) rc = sabc_get_state(e, eps, counters);
+    }
+    if (!rc) {
+        SABC_CUDA(cudaEventRecord(d, e->s_out));
+        SABC_CUDA(cudaEventSynchronize(d));
+        SABC_CUDA(cudaStreamSynchronize(e->s_in));
+        float t1 = 0, t2 = 0, t3 = 0;
+        cudaEventElapsedTime(&t1, a, b); cudaEventElapsedTime(&t2, c, d); cudaEventElapsedTime(&t3, a, d);
+        e->timing = t_upd;
+        e->timing.h2d_ms = t1; e->timing.d2h_ms = t2; e->timing.host_ms = t3;
+    } else {
+        cudaStreamSynchronize(e->s_in); cudaStreamSynchronize(e->s_out);
+    }
+    cleanup();
+    return rc;
 }
 
 int sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, double* eps, int64_t counters[4],

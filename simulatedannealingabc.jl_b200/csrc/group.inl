@@ -84,7 +84,7 @@ static void group_pull_state(sabc_engine* e) {           // every rank holds the
         e->timing.h2d_ms = std::max(e->timing.h2d_ms, ch->timing.h2d_ms);
         e->timing.d2h_ms = std::max(e->timing.d2h_ms, ch->timing.d2h_ms);
         e->timing.resample_ms = std::max(e->timing.resample_ms, ch->timing.resample_ms);
-        if (ch != c0) { e->timing.total_launches += ch->timing.total_launches; e->timing.kernel_launches += ch->timing.kernel_launches; e->timing.d2h_bytes += ch->timing.d2h_bytes; }
+        if (ch != c0) { e->timing.total_launches += ch->timing.total_launches; e->timing.kernel_launches += ch->timing.kernel_launches; }
     }
 }
 

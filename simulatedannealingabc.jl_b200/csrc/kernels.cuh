@@ -41,6 +41,12 @@ struct DevState {
 // ------------------------------------------------------------------------------------------------
 // shared device functions
 // ------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+// every kernel of the update sequence starts with this test: after an error (e.g. mean u <= eps() in update_epsilon_multi_eps,
+// :107-109) the state stays as it was at the failing update, like the reference's error() aborting there, although the captured
+// graph keeps replaying; `hold` is the multi-GPU resampling request (DevState)
+SABC_D bool halted(const DevState* ds) { return (ds->hold | ds->error_flag) != 0; }
+#endif
 
 // Accept rule, src/SimulatedAnnealingABC.jl:318-324.  uo/un stride through column-major rows.
 SABC_HD bool accept_rule(int s, const double* uo, int64_t ldo, const double* un, int64_t ldn, const double* eps,
@@ -162,7 +168,6 @@ struct PopView {                 // structure-of-arrays particle state of one GP
     double* rho;                 // [S][ld]
     double* lp;                  // [ld] cached logpdf(prior, θ_i)   (reference recomputes it, :318)
     int64_t ld;
-    unsigned char* dirty;        // [ld] or nullptr: set when the row accepts (host-buffer calls download only those rows)
 };
 
 struct UpdateArgs {
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(CHUNK, M::FUSED_MIN_BLOCKS) update_half_kernel
     __shared__ ZigEntry s_zig[256];
 
     const int tid = threadIdx.x;
-    if (a.ds->hold) return;
+    if (halted(a.ds)) return;
     for (int k = tid; k < 2 * S + 1; k += CHUNK) s_acc[k] = 0ull;
     if (PROP == PROP_RW) for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k];
     const uint32_t zig = stage_zig(s_zig);
@@ -328,7 +333,6 @@ __global__ void __launch_bounds__(CHUNK, M::FUSED_MIN_BLOCKS) update_half_kernel
 #pragma unroll
                 for (int j = 0; j < S; ++j) { a.pop.u[j * ld + gi] = up[j]; a.pop.rho[j * ld + gi] = rp[j]; }
                 a.pop.lp[gi] = lpp;
-                if (a.pop.dirty) a.pop.dirty[gi] = 1;
             } else {
 #pragma unroll
                 for (int j = 0; j < S; ++j) { up[j] = a.pop.u[j * ld + gi]; rp[j] = a.pop.rho[j * ld + gi]; }
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(CHUNK) propose_kernel(const UpdateArgs a, cons
     __shared__ double s_chol[PROP == PROP_RW ? D * D : 1];
     __shared__ ZigEntry s_zig[PROP == PROP_STRETCH ? 1 : 256];
     const int tid = threadIdx.x, lane = tid & 31;
-    if (a.ds->hold) return;
+    if (halted(a.ds)) return;
     if (PROP == PROP_RW) for (int k = tid; k < D * D; k += CHUNK) s_chol[k] = a.ds->chol[k];
     const uint32_t zig = PROP == PROP_STRETCH ? 0u : stage_zig(s_zig);
     __syncthreads();
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
     constexpr int D = M::D, S = M::S;
     extern __shared__ __align__(128) double s_top[];
     __shared__ ZigEntry s_zig[model_draws_normals<M>::value ? 256 : 1];
-    if (a.ds->hold) return;
+    if (halted(a.ds)) return;
     const uint32_t zig = model_draws_normals<M>::value ? stage_zig(s_zig) : 0u;
     stage_ecdf_top(a.ecdf, S, s_top);
     __syncthreads();
@@ -468,7 +472,6 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
 #pragma unroll
                 for (int j = 0; j < S; ++j) { a.pop.u[j * ld + gi] = up[j]; a.pop.rho[j * ld + gi] = rp[j]; }
                 a.pop.lp[gi] = lpp;
-                if (a.pop.dirty) a.pop.dirty[gi] = 1;
                 n_acc++;
             }
         }
@@ -525,7 +528,7 @@ static __global__ void __launch_bounds__(CHUNK) stats_kernel(PopView pop, int64_
     __shared__ unsigned long long s_acc[2 * MAX_S];
     __shared__ double s_w[8];
     const int tid = threadIdx.x;
-    if (ds->hold) return;
+    if (halted(ds)) return;
     for (int k = tid; k < 2 * S; k += CHUNK) s_acc[k] = 0ull;
     __syncthreads();
     const int64_t n_groups = (n + CHUNK - 1) / CHUNK;
@@ -596,7 +599,9 @@ __global__ void __launch_bounds__(CHUNK) init_prior_sim_kernel(const InitArgs a)
 // ------------------------------------------------------------------------------------------------
 // Model plug-in registry: one launcher table per model (the template instantiations above).
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t SABC_MODEL_VTABLE_VERSION = 2;
 struct ModelVTable {
+    uint32_t struct_size, abi_version;   // sizeof(ModelVTable), SABC_MODEL_VTABLE_VERSION of the headers the plug-in was compiled with
     const char* name;
     int32_t n_para, n_stats;
     cudaError_t (*launch_init)(const InitArgs&, int grid, cudaStream_t);
@@ -684,6 +689,7 @@ struct ModelLaunchers {
     }
     static ModelVTable vtable(const char* name, int heavy = 0) {
         ModelVTable v{};
+        v.struct_size = (uint32_t)sizeof(ModelVTable); v.abi_version = SABC_MODEL_VTABLE_VERSION;
         v.name = name; v.n_para = M::D; v.n_stats = M::S;
         v.launch_init = &init; v.launch_update = &update; v.update_occupancy = &occupancy; v.simulate = &simulate;
         v.heavy = heavy; v.key_bits = M::KEY_BITS; v.launch_propose = &propose; v.launch_simacc = &simacc; v.simacc_occupancy = &simacc_occ;

@@ -200,7 +200,7 @@ static int mg_resample(sabc_engine* e) {
     const int g_tiles = (int)std::min<int64_t>(n_tiles, (int64_t)e->n_sm * 8);
     // local weights and prefix sums
     k_weights<<<g_tiles, CHUNK, 0, e->stream>>>(e->pop, n, e->S, e->delta, ds, e->b_q.p, e->b_tile_sum.p, 1);
-    k_scan_tiles<<<1, 1024, 0, e->stream>>>(e->b_tile_sum.p, n_tiles, e->b_tile_off.p, &ds->w_total, ds, 1);
+    k_scan_tiles<<<1, 1024, 0, e->stream>>>(e->b_tile_sum.p, n_tiles, e->b_tile_off.p, &ds->w_total, ds, 2);
     k_prefix<<<g_tiles, CHUNK, 0, e->stream>>>(e->b_q.p, n, e->b_tile_off.p, ds, 1);
     SABC_CUDA(cudaGetLastError());
     std::vector<unsigned long long> w(G);
@@ -237,7 +237,7 @@ static __global__ void k_mg_pack_stats(const DevState* ds, int S, unsigned long 
 // every rank reduces the gathered statistics in rank order (integer sums exact, rho sums in one fixed order: identical on all
 // ranks), then takes the decision of :334-343.  A due resampling raises `hold`: see DevState.
 static __global__ void k_mg_decide(DevState* ds, const unsigned long long* all, int G, int S, int64_t n_global, int64_t resample) {
-    if (ds->hold) return;
+    if (halted(ds)) return;
     const int W = 4 * S + 1, t = threadIdx.x;
     if (t < S) {
         unsigned long long hi = 0, lo = 0;

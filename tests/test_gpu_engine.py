@@ -326,3 +326,43 @@ def test_full_size_parity_vs_oracle(gpu, name, N, alg):
     cnt = eng.get_state()[1]
     assert cnt[0] == 4 * N and cnt[3] == 3 and cnt[2] >= 2, cnt           # at least one resampling after the initial one
     eng.close(); orc.close()
+
+
+def test_zero_weights_fail_loudly_and_the_error_does_not_stick(gpu):
+    """delta so large that every 32.32 fixed-point resampling weight flushes to zero: the single-GPU path reports it (like the sharded
+    one) instead of collapsing the population onto one particle, and the next call -- with a sane delta -- runs (the error flag is
+    cleared at the start of every call)."""
+    model, prior = model_cases()["gauss_sample_d2s2"]
+    for n in (3000, 40_000):                                    # single-CTA tail and generic tail
+        eng = sb.Engine(model, prior, n_particles=n, algorithm="single_eps", proposal=DE(2), resample=n // 4, v=1.0, delta=1e6)
+        with pytest.raises(sb.SABCError) as ei:
+            eng.init()                                           # the initial resampling already has all-zero weights
+        assert ei.value.code == -20 and "weights are zero" in str(ei.value)
+        eng2 = sb.Engine(model, prior, n_particles=n, algorithm="single_eps", proposal=DE(2), resample=n // 4, v=1.0, delta=0.1)
+        eng2.init(); eng2.update(3 * n)
+        before = [a.copy() for a in eng2.get_population()]
+        eng2.set_tuning(1.0, 1e6, n // 4, DE(2))
+        with pytest.raises(sb.SABCError):
+            eng2.update(30 * n)                                  # a resampling falls into this call
+        eng2.set_tuning(1.0, 0.1, n // 4, DE(2))
+        eng2.update(3 * n)                                       # not sticky
+        assert eng2.get_state()[1][3] >= 6 and not all(np.array_equal(a, b) for a, b in zip(before, eng2.get_population()))
+
+
+def test_rho_mean_of_a_very_large_population(gpu):
+    """1.25e8 particles with two statistics: the radix-256 tree sums of the columns run concurrently, one CTA per column, each with
+    its own scratch for ALL tree levels (a scratch sized for the first level only let column j's third level overwrite column j+1's
+    second one beyond 1.2e8 particles).  rho_history[0] must equal the mean of the downloaded prior distances."""
+    import ctypes as C
+    free, total = C.c_size_t(), C.c_size_t()
+    cudart = C.CDLL("libcudart.so")
+    if cudart.cudaMemGetInfo(C.byref(free), C.byref(total)) != 0 or free.value < 60e9:
+        pytest.skip("needs 60 GB of free device memory")
+    model, prior = model_cases()["gauss_sample_d2s2"]
+    N = 125_000_000
+    eng = sb.Engine(model, prior, n_particles=N, algorithm="multi_eps", proposal=DE(2), resample=2 * N, v=1.0, delta=0.1)
+    eng.init()
+    rho = eng.get_population(theta=False, u=False)[2]
+    rh = eng.get_history()[2]
+    assert np.allclose(rh[0], rho.mean(axis=0), rtol=1e-11, atol=0), (rh[0], rho.mean(axis=0))
+    eng.close()

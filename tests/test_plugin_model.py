@@ -59,3 +59,33 @@ def test_plugin_runs_on_the_engine(gpu, plugin):
         res = sb.sabc(model, prior, n_particles=2000, n_simulation=60_000, algorithm=algorithm)
         assert res.state.n_population_updates == 29 and np.all(res.state.eps < 0.5) and np.all(np.isfinite(res.population))
         assert abs(np.median(res.population[:, 0]) - 0.4) < 0.35       # obs correspond to phi ~ 0.4, sigma ~ 0.9
+
+
+def test_register_rejects_a_foreign_launch_table(plugin):
+    """the launch table carries its own size and version: a plug-in compiled against other kernel headers is refused, not called"""
+    bogus = (C.c_uint32 * 64)()
+    bogus[0], bogus[1] = 8, 1
+    assert sb._lib.lib().sabc_register_model(bogus) == -20
+    assert b"launch table" in sb._lib.lib().sabc_last_error()
+
+
+@pytest.mark.gpu
+def test_engine_survives_a_plugin_loaded_later(gpu):
+    """an engine keeps a pointer to its model's registry entry; loading a plug-in afterwards (dlopen -> sabc_register_model) must not
+    move that entry.  Separate process: the plug-in must not be loaded yet when the engine is created."""
+    code = f"""
+import ctypes as C, sys
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+import numpy as np, sabc_b200 as sb
+kw = dict(n_particles=2000, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=1), resample=4000, v=1.0, delta=0.1)
+a = sb.Engine(sb.models.gauss_mean(1.0), sb.Normal(0, 1), **kw); a.init(); a.update(5 * 2000)
+n0 = sb._lib.lib().sabc_model_count()
+C.CDLL({os.path.join(PLUGIN_DIR, 'libsabc_ar1.so')!r}, mode=C.RTLD_GLOBAL)
+assert sb._lib.lib().sabc_model_count() == n0 + 1
+a.update(5 * 2000)
+b = sb.Engine(sb.models.gauss_mean(1.0), sb.Normal(0, 1), **kw); b.init(); b.update(10 * 2000)
+assert all(np.array_equal(x, y) for x, y in zip(a.get_population(), b.get_population()))
+print("ok")
+"""
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
