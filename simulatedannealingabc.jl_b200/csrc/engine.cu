@@ -480,6 +480,8 @@ extern "C" int sabc_mg_exchange_plan(const int64_t* counts, int32_t world, int64
     return 0;
 }
 
+static int ecdf_attach(sabc_engine* e, int j, DevBuf<double>* knots, int64_t L, int top_max);
+static int top_max_for(int S);
 #include "multi_gpu.inl"
 
 extern "C" {
@@ -740,11 +742,17 @@ int sabc_init(sabc_engine* e) {
         DevBuf<double> keys, gathered;
         DevBuf<unsigned char> cub_tmp;
         DevBuf<unsigned long long> cnt;
-        SABC_CUDA(keys.alloc((size_t)e->N)); SABC_CUDA(cnt.alloc(1));
-        if (e->sharded()) SABC_CUDA(gathered.alloc((size_t)e->N));
+        SABC_CUDA(cnt.alloc(1));
         for (int j = 0; j < e->S; ++j) {
             const double* col = e->pop.rho + (int64_t)j * e->pop.ld;
-            if (e->sharded()) { SABC_TRY(mg_allgather_f64(e, col, gathered.p, n)); col = gathered.p; }
+            if (e->sharded() && e->ecdf_max_knots >= 2) {
+                // compressed ECDF over a sharded population: the K global quantiles by a distributed selection, O(N / G) per rank
+                int done = 0;
+                SABC_TRY(mg_ecdf_quantiles(e, j, col, keys, cub_tmp, cnt, &done));
+                if (done) continue;
+            }
+            SABC_CUDA(keys.ensure((size_t)e->N));
+            if (e->sharded()) { SABC_CUDA(gathered.ensure((size_t)e->N)); SABC_TRY(mg_allgather_f64(e, col, gathered.p, n)); col = gathered.p; }
             SABC_TRY(ecdf_build_column(e, j, col, e->N, keys, cub_tmp, cnt));
         }
     }

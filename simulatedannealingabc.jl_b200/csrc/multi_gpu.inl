@@ -105,6 +105,90 @@ static int mg_warm_p2p(sabc_engine* e) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Compressed ECDF over a sharded population (multi-GPU half): the table keeps the K rank-uniform
+// quantiles x[floor(i (m-1) / (K-1))] of the m GLOBAL positive prior distances.  No rank ever holds the global column: every
+// rank sorts its own slice, and the K order statistics are found by K simultaneous bisections on the 64-bit pattern of the value
+// (monotone for positive doubles) -- each step counts the local entries <= the K candidates by binary search and all-reduces the
+// K counts.  64 steps of a K-word all-reduce instead of an all-gather of 8 N bytes and a sort of N values on every rank; the
+// knots equal the single-GPU compressed table for the same K bit for bit (tests/test_gpu_multi.py).
+// ------------------------------------------------------------------------------------------------
+static __global__ void k_q_init(int K, int64_t m, unsigned long long* lo, unsigned long long* hi, long long* target) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+        lo[i] = 0ull; hi[i] = 0x7fefffffffffffffull;                       // [+0, largest finite]
+        target[i] = (long long)(((int64_t)i * (m - 1)) / (int64_t)(K - 1)) + 1;   // rank (1-based) of quantile i
+    }
+}
+// number of local sorted positives <= the mid-point candidate of every bisection
+static __global__ void k_q_count(int K, const double* sorted, int64_t n_pos, const unsigned long long* lo, const unsigned long long* hi,
+                                 long long* cnt) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+        const double v = __longlong_as_double((long long)(lo[i] + (hi[i] - lo[i]) / 2));
+        int64_t a = 0, len = n_pos;                                           // first index with sorted[idx] > v
+        while (len > 0) { const int64_t h = len >> 1; if (sorted[a + h] <= v) { a += h + 1; len -= h + 1; } else len = h; }
+        cnt[i] = (long long)a;
+    }
+}
+static __global__ void k_q_step(int K, unsigned long long* lo, unsigned long long* hi, const long long* cnt, const long long* target) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+        const unsigned long long mid = lo[i] + (hi[i] - lo[i]) / 2;
+        if (cnt[i] >= target[i]) hi[i] = mid; else lo[i] = mid + 1;
+    }
+}
+static __global__ void k_q_knots(int K, const unsigned long long* lo, double* out /* K + 2 + ECDF_PAD */) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K + 2 + ECDF_PAD; i += gridDim.x * blockDim.x) {
+        double v;
+        if (i == 0) v = 0.0;
+        else if (i <= K) v = __longlong_as_double((long long)lo[i - 1]);
+        else if (i == K + 1) v = __longlong_as_double((long long)lo[K - 1]) * 1.5;
+        else v = dinf();
+        out[i] = v;
+    }
+}
+static int mg_ecdf_quantiles(sabc_engine* e, int j, const double* d_col, DevBuf<double>& keys, DevBuf<unsigned char>& cub_tmp,
+                             DevBuf<unsigned long long>& cnt, int* done) {
+    *done = 0;
+    const int64_t n = e->n_local;
+    const int K = e->ecdf_max_knots;
+    SABC_CUDA(keys.ensure((size_t)2 * n));                                      // marked keys | sorted keys
+    double* sorted = keys.p + n;
+    SABC_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), e->stream));
+    k_mark_positive<<<(int)std::min<int64_t>((n + 255) / 256, 8192), 256, 0, e->stream>>>(d_col, n, keys.p, cnt.p);
+    SABC_CUDA(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    SABC_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys.p, sorted, (int64_t)n, 0, 64, e->stream));
+    SABC_CUDA(cub_tmp.ensure(tmp_bytes));
+    SABC_CUDA(cub::DeviceRadixSort::SortKeys(cub_tmp.p, tmp_bytes, keys.p, sorted, (int64_t)n, 0, 64, e->stream));
+    unsigned long long n_pos_local = 0, m = 0;
+    SABC_CUDA(cudaMemcpyAsync(&n_pos_local, cnt.p, sizeof n_pos_local, cudaMemcpyDeviceToHost, e->stream));
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    std::vector<unsigned long long> all(e->world);
+    SABC_TRY(mg_allgather_u64_host(e, cnt.p, all.data()));
+    for (auto v : all) m += v;
+    if (m == 0) return set_error(SABC_ERR_NO_POSITIVE, "build_cdf: statistic %d has no positive prior distance", j + 1);
+    if ((int64_t)m <= K) return 0;                                               // the whole sample is kept: the general path builds it
+    DevBuf<unsigned long long> lo, hi;
+    DevBuf<long long> target, c;
+    SABC_CUDA(lo.alloc(K)); SABC_CUDA(hi.alloc(K)); SABC_CUDA(target.alloc(K)); SABC_CUDA(c.alloc(K));
+    const int grid = (K + 255) / 256;
+    k_q_init<<<grid, 256, 0, e->stream>>>(K, (int64_t)m, lo.p, hi.p, target.p);
+    for (int it = 0; it < 64; ++it) {
+        k_q_count<<<grid, 256, 0, e->stream>>>(K, sorted, (int64_t)n_pos_local, lo.p, hi.p, c.p);
+        SABC_CUDA(cudaGetLastError());
+        SABC_NCCL(nccl_api()->AllReduce(c.p, c.p, (size_t)K, ncclInt64, ncclSum, e->comm.comm, e->stream));
+        k_q_step<<<grid, 256, 0, e->stream>>>(K, lo.p, hi.p, c.p, target.p);
+    }
+    auto* small = new DevBuf<double>();
+    e->ecdf_bufs.push_back(small);
+    SABC_CUDA(small->alloc((size_t)K + 2 + ECDF_PAD));
+    k_q_knots<<<(K + 2 + ECDF_PAD + 255) / 256, 256, 0, e->stream>>>(K, lo.p, small->p);
+    SABC_CUDA(cudaGetLastError());
+    SABC_CUDA(cudaStreamSynchronize(e->stream));
+    SABC_TRY(ecdf_attach(e, j, small, (int64_t)K + 2, std::max(top_max_for(e->S), pow2_ceil(K + 2))));
+    *done = 1;
+    return 0;
+}
+
 // the surplus exchange: rank g's packed selection occupies the global slots [C_g, C_g + c_g), rank d owns [d n, (d+1) n);
 // only what crosses a slice boundary travels (grouped ncclSend/ncclRecv), then the statistics of the new population
 static int mg_exchange_selection(sabc_engine* e, const std::vector<int64_t>& counts, int64_t sb_ld) {

@@ -132,6 +132,26 @@ if rank == 0:
     assert stats.ks_2samp(all_u2[:, 0], u1[:, 0]).pvalue > 1e-3
 eng.close(); eng2.close()
 
+# compressed ECDF over a sharded population: the K global quantiles come from a distributed selection (no rank holds the global
+# column); the knots must equal the single-GPU compressed table for the same K bit for bit
+for name, K in (("gauss_sample_d2s2", 510), ("sir_tauleap", 1022)):
+    model, prior = model_cases()[name]
+    N = 6000 * world
+    kw = dict(n_particles=N, algorithm="single_eps", proposal=sb.DifferentialEvolution(n_para=model.n_para), resample=N, v=1.0, delta=0.1,
+              ecdf_max_knots=K, seed=21)
+    comm = new_comm()
+    engk = sb.Engine(model, prior, device=int(os.environ["LOCAL_RANK"]), rank=comm[0], world_size=comm[1], nccl_unique_id=comm[2], **kw)
+    engk.init()
+    if rank == 0:
+        one = sb.Engine(model, prior, device=int(os.environ["LOCAL_RANK"]), **kw); one.init()
+        for j in range(model.n_stats):
+            a, b = engk.get_ecdf(j), one.get_ecdf(j)
+            assert a.size == b.size <= K + 2 and np.array_equal(a, b), (name, j, a.size, b.size, int((a != b).sum()))
+        one.close()
+    engk.update(5 * N)
+    ks = gather(engk.get_ecdf(0)); assert all(np.array_equal(k, ks[0]) for k in ks)
+    engk.close()
+
 # posterior of C1 over the sharded population (slow annealing): mean and variance within 2 MC standard errors of N(10/11, 1/11),
 # the MC error estimated from independent runs (north_star check 3)
 model, prior = model_cases()["gauss_mean"]
