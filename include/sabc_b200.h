@@ -192,6 +192,10 @@ int  sabc_propose(int32_t proposal, const double* prop_par, int32_t d, const dou
 int  sabc_mg_exchange_plan(const int64_t* counts, int32_t world, int64_t n_local, int32_t me, int64_t* send_off,
                            int64_t* send_cnt, int64_t* recv_off, int64_t* recv_cnt);
 
+/* host-side split of the N resampling draws over the ranks of a sharded population (pure function, needs no device): counts[g] ~
+ * Multinomial(n_draws; w[g] / sum w) from the shared seed and the resampling count, the same vector on every rank */
+int  sabc_multinomial_split(int64_t n_draws, const uint64_t* w, int32_t world, uint64_t seed, uint32_t resample_count, int64_t* counts_out);
+
 /* ---- device model plug-in registry (new; the GPU form of f_dist) ---- */
 /* `vtable` points to a sabc::ModelVTable (csrc/kernels.cuh) built by an out-of-tree .cu that includes
  * the header-only kernel templates; typically called from a static initialiser at dlopen time. */

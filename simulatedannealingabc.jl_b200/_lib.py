@@ -97,6 +97,7 @@ SYMBOLS = {
     "sabc_model_info": (C.c_int, [C.c_char_p, c_int32_p, c_int32_p]),
     "sabc_propose": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
     "sabc_mg_exchange_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sabc_multinomial_split": (C.c_int, [C.c_int64, C.c_void_p, C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p]),
     "sabc_register_model": (C.c_int, [C.c_void_p]),
     "sabc_model_count": (C.c_int, []),
     "sabc_model_name": (C.c_char_p, [C.c_int]),

@@ -482,6 +482,13 @@ extern "C" int sabc_mg_exchange_plan(const int64_t* counts, int32_t world, int64
 
 static int ecdf_attach(sabc_engine* e, int j, DevBuf<double>* knots, int64_t L, int top_max);
 static int top_max_for(int S);
+extern "C" int sabc_multinomial_split(int64_t n_draws, const uint64_t* w, int32_t world, uint64_t seed, uint32_t resample_count,
+                                      int64_t* counts_out) {
+    if (!w || !counts_out || world < 1 || n_draws < 0) return set_error(SABC_ERR_INVALID, "bad multinomial-split argument");
+    multinomial_split(n_draws, (const unsigned long long*)w, world, seed, resample_count, counts_out);
+    return 0;
+}
+
 #include "multi_gpu.inl"
 
 extern "C" {

@@ -413,12 +413,15 @@ struct SirTauLeap {
     // per-lane state machine over sampler ATTEMPTS (phase 0/1/2 = the three draws of a step): every loop trip each
     // lane makes one attempt on its own current draw, so a PTRS rejection costs that lane one trip instead of
     // stalling the whole warp.  The blocks a particle consumes, and hence its result, are those of the plain
-    // sequential loop over steps and draws.
+    // sequential loop over steps and draws.  (Measured and rejected: parking the lanes that need the exact PTRS test or the
+    // inversion loop, r1 notes; persistent lanes that take the next particle as soon as theirs is finished, with the ECDF /
+    // accept epilogue as a separate convergent kernel -- 0.845 ms against 0.783 per half-sweep, the live lanes per instruction
+    // did not rise: the idle lanes sit inside a trip, in the divergent sampler branches, not behind finished particles;
+    // profiles/r2_notes.md.)
     SABC_HD static void sim(const double (&th)[4], const ModelPar& mp, Stream& st, double (&rho)[3]) {
         const double pop = mp.v[0], tau = mp.v[2];
         const double inv_pop = drcp(pop);
         const int T = (int)mp.v[1];
-        // compartments and counts are integers below 2^53 held in FP64: exact, and no int64 <-> double conversions in the loop
         const double popi = (double)(int64_t)pop;
         double I = floor(th[2] * pop + 0.5);
         if (I < 0.0) I = 0.0;
@@ -428,8 +431,7 @@ struct SirTauLeap {
         int tpeak = 0;
         int t = 1, phase = 0;
         double lam = (((th[0] * Sc) * I) * inv_pop) * tau;
-        // one accepted draw k moves the particle to its next draw
-        auto advance = [&](double k) {
+        auto advance = [&](double k) {       // one accepted draw k moves the particle to its next draw
             if (phase == 0) {
                 ninf = k > Sc ? Sc : k;
                 lam = (th[1] * I) * tau;
@@ -446,9 +448,6 @@ struct SirTauLeap {
                 phase = 0; t++;
             }
         };
-        // Every loop trip each lane makes ONE sampler attempt on its own current draw, so a PTRS rejection costs that lane
-        // one trip instead of stalling its warp.  (Parking the lanes that need the exact PTRS test or the inversion loop
-        // until enough of them wait was measured and is slower: the cheap part of a trip is not cheap enough, r1 notes.)
         while (t <= T) {
             double k;
             if (!poisson_attempt_d(lam, st, k)) continue;

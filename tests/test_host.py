@@ -167,3 +167,38 @@ def test_prior_constructors_validate_like_distributions_jl():
     assert len(p) == 3 and [c.kind for c in p.components()] == [4, 5, 0] and p.components()[0].params() == (2.0, 0.5)
     with pytest.raises(TypeError):
         sb.product_distribution([sb.Gamma(2.0, 0.5), "Normal(0,1)"])
+
+
+def test_multinomial_split_counts_are_multinomial():
+    """the per-rank counts of the sharded resampling: sum to N, deterministic in (seed, resampling count), and each marginal is the
+    Binomial(N, w_g / W) it must be (chi-square against scipy over many resampling counts), for weights from balanced to extreme."""
+    from scipy import stats
+    lib = sb._lib.lib()
+    for N, w in ((100_000, [3, 1, 1, 1]), (1000, [1, 1]), (37, [5, 1, 0, 2]), (10_000_000, [2**40, 2**40 + 12345, 2**39, 2**41, 1, 2**40, 2**40, 2**40]),
+                 (5000, [10**6, 1])):
+        w = np.array(w, dtype=np.uint64); G = w.size
+        reps = 4000 if N <= 100_000 else 600
+        out = np.zeros((reps, G), dtype=np.int64)
+        for r in range(reps):
+            assert lib.sabc_multinomial_split(N, sb._lib.ptr(w), G, 0x5ABC, r, sb._lib.ptr(out[r])) == 0
+        assert np.all(out.sum(axis=1) == N) and np.all(out >= 0)
+        again = np.zeros(G, dtype=np.int64)
+        lib.sabc_multinomial_split(N, sb._lib.ptr(w), G, 0x5ABC, 7, sb._lib.ptr(again))
+        assert np.array_equal(again, out[7])
+        p = w.astype(np.float64) / w.astype(np.float64).sum()
+        for g in range(G):
+            if p[g] == 0:
+                assert np.all(out[:, g] == 0)
+                continue
+            m, v = N * p[g], N * p[g] * (1 - p[g])
+            assert abs(out[:, g].mean() - m) < 5 * np.sqrt(v / reps) + 1e-9, (N, g, out[:, g].mean(), m)
+            if v > 1:
+                assert 0.85 < out[:, g].var() / v < 1.15, (N, g, out[:, g].var(), v)
+            if N <= 1000:                                   # full chi-square of the marginal
+                lo, hi = out[:, g].min(), out[:, g].max()
+                obs = np.bincount(out[:, g] - lo, minlength=hi - lo + 1).astype(float)
+                exp = stats.binom(N, p[g]).pmf(np.arange(lo, hi + 1)) * reps
+                keep = exp >= 5
+                o = np.append(obs[keep], obs[~keep].sum()); e = np.append(exp[keep], reps - exp[keep].sum())
+                chi = ((o - e) ** 2 / np.maximum(e, 1e-9)).sum()
+                assert stats.chi2.sf(chi, o.size - 1) > 1e-4, (N, g, chi)
