@@ -40,9 +40,14 @@ static __global__ void k_ecdf_level(const double* in, int64_t cnt, int64_t n_nod
     }
     for (int64_t i = t0; i < next_len; i += stride) next[i] = i < n_nodes ? in[i * ECDF_STRIDE] : dinf();
 }
-static __global__ void k_copy_pad_inf(const double* in, int64_t cnt, double* out, int64_t len) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = i < cnt ? in[i] : dinf();
+// the staged top level: `len` entries (+inf beyond cnt) stored as len high words followed by len low words
+static __global__ void k_top_split(const double* in, int64_t cnt, double* out, int64_t len) {
+    uint32_t* hi = reinterpret_cast<uint32_t*>(out);
+    uint32_t* lo = hi + len;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = f64_bits(i < cnt ? in[i] : dinf());
+        hi[i] = (uint32_t)(b >> 32); lo[i] = (uint32_t)b;
+    }
 }
 // compressed ECDF: K rank-uniform quantiles x[floor(i (m-1)/(K-1))], i = 0..K-1, of the m sorted positive distances
 static __global__ void k_ecdf_subsample(const double* sorted_pos, int64_t m, int K, double* out /* K + 2 + ECDF_PAD */) {

@@ -37,7 +37,7 @@ inline int ecdf_build_index(EcdfStat& st, const double* d_knots, int64_t L, int 
     st.top_cnt = (int)cnt; st.top_pow2 = pow2_ceil(cnt);
     auto* top = new DevBuf<double>(); bufs.push_back(top);
     SABC_CUDA(top->alloc((size_t)st.top_pow2));
-    k_copy_pad_inf<<<grid_of(st.top_pow2), 256, 0, stream>>>(cur, cnt, top->p, st.top_pow2);
+    k_top_split<<<grid_of(st.top_pow2), 256, 0, stream>>>(cur, cnt, top->p, st.top_pow2);
     SABC_CUDA(cudaGetLastError());
     st.top = top->p;
     SABC_CUDA(cudaStreamSynchronize(stream));

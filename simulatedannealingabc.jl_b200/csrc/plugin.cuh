@@ -255,7 +255,8 @@ constexpr int ECDF_STRIDE = 9;      // level k+1 samples every 9th entry of leve
 struct EcdfStat {
     const double* knots;                      // K[0..L), natural order (returned by sabc_get_ecdf; not read by the lookup)
     const double* node[ECDF_MAX_LEVELS];      // node[k]: probe-ordered nodes for the search inside level k, k = 0 .. nlev-2
-    const double* top;                        // top level, natural order, top_pow2 entries (+inf padded)
+    const double* top;                        // top level, natural order, top_pow2 entries (+inf padded), stored SPLIT: the high 32-bit
+                                              // words of all entries, then the low words (same bytes; see ecdf_eval)
     int64_t L;
     double kmax;                              // K[L-1]
     int32_t nlev;                             // levels incl. the knots; level nlev-1 is the staged one
@@ -278,15 +279,33 @@ SABC_HD int64_t count_less(const double* a, int64_t n, double x) {
 SABC_D bool log_u_less(double U, double L) { return det_log(U) < L; }
 
 SABC_D double ecdf_eval(const EcdfStat& e, const double* s_top, double rho) {
-    const double x = rho > e.kmax ? e.kmax : (rho < 0.0 ? 0.0 : rho);        // Flat(): clamp to [K_1, K_L]
-    // searchsortedfirst on the staged top level: branch-free bisection over a power-of-two table padded with +inf
-    const double* T = s_top + e.top_off;
+    double x = rho > e.kmax ? e.kmax : (rho < 0.0 ? 0.0 : rho);              // Flat(): clamp to [K_1, K_L]
+    if (!(x == x)) return x;                                                  // NaN distance: u = 0 + m (NaN - 0)
+    x = x + 0.0;                                                              // -0.0 -> +0.0: from here on x orders like its bit pattern
+    // searchsortedfirst on the staged top level: bisection over a power-of-two table padded with +inf.  The table is staged as
+    // 32-bit words (all high words, then all low words) and compared as integers -- non-negative doubles order like their bit
+    // patterns: 32 lanes reading random 8-byte entries cost 10-20 shared-memory wavefronts per step (bank conflicts), random 4-byte
+    // words 3-4; the low word is only read when the high words tie.
+    const uint32_t* Th = reinterpret_cast<const uint32_t*>(s_top + e.top_off);
+    const uint32_t* Tl = Th + e.top_pow2;
+    const uint32_t xh = (uint32_t)(f64_bits(x) >> 32), xl = (uint32_t)f64_bits(x);
     int c = 0;
-    for (int step = e.top_pow2 >> 1; step >= 1; step >>= 1) c += (T[c + step - 1] < x) ? step : 0;
-    c += (T[c] < x) ? 1 : 0;
-    // no knot below x: x is K_1 = 0 (or NaN), the bracket is the first interval and u = 0 + m (x - 0)
-    if (c == 0) return x + 0.0;
-    double lo = T[c - 1], hi = c < e.top_pow2 ? T[c] : dinf();               // A[c-1] < x <= A[c]
+    for (int step = e.top_pow2 >> 1; step >= 1; step >>= 1) {
+        const uint32_t th = Th[c + step - 1];
+        bool lt = th < xh;
+        if (th == xh) lt = Tl[c + step - 1] < xl;
+        c += lt ? step : 0;
+    }
+    {
+        const uint32_t th = Th[c];
+        bool lt = th < xh;
+        if (th == xh) lt = Tl[c] < xl;
+        c += lt ? 1 : 0;
+    }
+    // no knot below x: x is K_1 = 0, the bracket is the first interval and u = 0 + m (0 - 0)
+    if (c == 0) return 0.0;
+    double lo = bits_f64(((uint64_t)Th[c - 1] << 32) | Tl[c - 1]);
+    double hi = c < e.top_pow2 ? bits_f64(((uint64_t)Th[c] << 32) | Tl[c]) : dinf();   // A[c-1] < x <= A[c]
     int64_t lb = c;
     for (int lv = e.nlev - 2; lv >= 0; --lv) {
         const double2* nd = reinterpret_cast<const double2*>(e.node[lv] + (lb - 1) * ECDF_NODE);
