@@ -318,9 +318,9 @@ __global__ void __launch_bounds__(CHUNK, M::FUSED_MIN_BLOCKS) update_half_kernel
                 Stream st(a.seed, pid, sweep, KIND_MODEL, nullptr, zig);
                 M::sim(thp, a.mp, st, rp);                              // :315
                 double Ssum = 0.0;
+                ecdf_eval_all<S>(a.ecdf, s_top, rp, up);                // :316
 #pragma unroll
                 for (int j = 0; j < S; ++j) {
-                    up[j] = ecdf_eval(a.ecdf[j], s_top, rp[j]);         // :316
                     const double t = (a.pop.u[j * ld + gi] - up[j]) / eps[j];
                     Ssum = (j == 0) ? t : Ssum + t;
                 }
@@ -457,9 +457,9 @@ __global__ void __launch_bounds__(CHUNK, M::SIM_MIN_BLOCKS) simulate_accept_kern
             st.warp_mask = live;
             M::sim(thp, a.mp, st, rp);                                  // :315
             double Ssum = 0.0;
+            ecdf_eval_all<S>(a.ecdf, s_top, rp, up);                    // :316
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                up[j] = ecdf_eval(a.ecdf[j], s_top, rp[j]);             // :316
                 const double t = (a.pop.u[j * ld + gi] - up[j]) / eps[j];
                 Ssum = (j == 0) ? t : Ssum + t;
             }

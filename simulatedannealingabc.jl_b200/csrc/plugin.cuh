@@ -278,10 +278,18 @@ SABC_HD int64_t count_less(const double* a, int64_t n, double x) {
 // the Metropolis test log(U) < L  (src/SimulatedAnnealingABC.jl:324)
 SABC_D bool log_u_less(double U, double L) { return det_log(U) < L; }
 
-SABC_D double ecdf_eval(const EcdfStat& e, const double* s_top, double rho) {
+// The lookup in three stages, so that the lookups of several statistics of one particle can be interleaved (ecdf_eval_all):
+// the dependent loads of one lookup (12 shared-memory steps, then two global probes per level) are what a simulation-heavy
+// model with many statistics waits for -- the logistic model's 20 lookups per particle ran at 9 % issue-slot utilisation as a
+// chain of 160 dependent loads; interleaved, CH independent chains are in flight per thread.
+struct EcdfCursor { double x, lo, hi; int64_t lb; };
+
+SABC_D void ecdf_top_search(const EcdfStat& e, const double* s_top, double rho, EcdfCursor& q) {
     double x = rho > e.kmax ? e.kmax : (rho < 0.0 ? 0.0 : rho);              // Flat(): clamp to [K_1, K_L]
-    if (!(x == x)) return x;                                                  // NaN distance: u = 0 + m (NaN - 0)
+    q.x = x; q.lb = 0; q.lo = 0.0; q.hi = 0.0;
+    if (!(x == x)) return;                                                    // NaN distance: handled by ecdf_finish
     x = x + 0.0;                                                              // -0.0 -> +0.0: from here on x orders like its bit pattern
+    q.x = x;
     // searchsortedfirst on the staged top level: bisection over a power-of-two table padded with +inf.  The table is staged as
     // 32-bit words (all high words, then all low words) and compared as integers -- non-negative doubles order like their bit
     // patterns: 32 lanes reading random 8-byte entries cost 10-20 shared-memory wavefronts per step (bank conflicts), random 4-byte
@@ -302,27 +310,60 @@ SABC_D double ecdf_eval(const EcdfStat& e, const double* s_top, double rho) {
         if (th == xh) lt = Tl[c] < xl;
         c += lt ? 1 : 0;
     }
-    // no knot below x: x is K_1 = 0, the bracket is the first interval and u = 0 + m (0 - 0)
-    if (c == 0) return 0.0;
-    double lo = bits_f64(((uint64_t)Th[c - 1] << 32) | Tl[c - 1]);
-    double hi = c < e.top_pow2 ? bits_f64(((uint64_t)Th[c] << 32) | Tl[c]) : dinf();   // A[c-1] < x <= A[c]
-    int64_t lb = c;
-    for (int lv = e.nlev - 2; lv >= 0; --lv) {
-        const double2* nd = reinterpret_cast<const double2*>(e.node[lv] + (lb - 1) * ECDF_NODE);
-        const double2 s = __ldg(nd);                                          // (e3, e6)
-        const int c1 = (s.x < x ? 1 : 0) + (s.y < x ? 1 : 0);
-        const double2 p = __ldg(nd + 1 + c1);                                 // (e1,e2) | (e4,e5) | (e7,e8)
-        const int c2 = (p.x < x ? 1 : 0) + (p.y < x ? 1 : 0);
-        const double lo_s = c1 == 0 ? lo : (c1 == 1 ? s.x : s.y), hi_s = c1 == 0 ? s.x : (c1 == 1 ? s.y : hi);
-        lo = c2 == 0 ? lo_s : (c2 == 1 ? p.x : p.y);
-        hi = c2 == 0 ? p.x : (c2 == 1 ? p.y : hi_s);
-        lb = (lb - 1) * ECDF_STRIDE + 1 + 3 * c1 + c2;
-    }
-    const int64_t j = lb - 1;                                                 // k > 1 && (k -= 1); lo = K[j], hi = K[j+1]
+    if (c == 0) return;                                                       // no knot below x: x is K_1 = 0
+    q.lo = bits_f64(((uint64_t)Th[c - 1] << 32) | Tl[c - 1]);
+    q.hi = c < e.top_pow2 ? bits_f64(((uint64_t)Th[c] << 32) | Tl[c]) : dinf();   // A[c-1] < x <= A[c]
+    q.lb = c;
+}
+// one level down: the two 16-byte probes of the node below entry lb - 1
+SABC_D void ecdf_descend(const EcdfStat& e, int lv, EcdfCursor& q) {
+    const double2* nd = reinterpret_cast<const double2*>(e.node[lv] + (q.lb - 1) * ECDF_NODE);
+    const double x = q.x;
+    const double2 s = __ldg(nd);                                              // (e3, e6)
+    const int c1 = (s.x < x ? 1 : 0) + (s.y < x ? 1 : 0);
+    const double2 p = __ldg(nd + 1 + c1);                                     // (e1,e2) | (e4,e5) | (e7,e8)
+    const int c2 = (p.x < x ? 1 : 0) + (p.y < x ? 1 : 0);
+    const double lo_s = c1 == 0 ? q.lo : (c1 == 1 ? s.x : s.y), hi_s = c1 == 0 ? s.x : (c1 == 1 ? s.y : q.hi);
+    q.lo = c2 == 0 ? lo_s : (c2 == 1 ? p.x : p.y);
+    q.hi = c2 == 0 ? p.x : (c2 == 1 ? p.y : hi_s);
+    q.lb = (q.lb - 1) * ECDF_STRIDE + 1 + 3 * c1 + c2;
+}
+SABC_D double ecdf_finish(const EcdfStat& e, const EcdfCursor& q) {
+    if (!(q.x == q.x)) return q.x;                                            // u = 0 + m (NaN - 0)
+    if (q.lb == 0) return 0.0;                                                // first interval: u = 0 + m (0 - 0)
+    const int64_t j = q.lb - 1;                                               // k > 1 && (k -= 1); lo = K[j], hi = K[j+1]
     const double Lm1 = (double)(e.L - 1);
     const double y0 = (double)j / Lm1, y1 = (double)(j + 1) / Lm1;           // range(0, stop=1, length=L)
-    const double m = (y1 - y0) / (hi - lo);
-    return y0 + m * (x - lo);
+    const double m = (y1 - y0) / (q.hi - q.lo);
+    return y0 + m * (q.x - q.lo);
+}
+SABC_D double ecdf_eval(const EcdfStat& e, const double* s_top, double rho) {
+    EcdfCursor q;
+    ecdf_top_search(e, s_top, rho, q);
+    if (q.lb > 0)
+        for (int lv = e.nlev - 2; lv >= 0; --lv) ecdf_descend(e, lv, q);
+    return ecdf_finish(e, q);
+}
+// u[j] = G_j(rho[j]) for the S statistics of one particle, CH lookups at a time with their loads interleaved
+template <int S>
+SABC_D void ecdf_eval_all(const EcdfStat* e, const double* s_top, const double (&rho)[S], double (&u)[S]) {
+    constexpr int CH = S < 4 ? S : 4;
+#pragma unroll
+    for (int j0 = 0; j0 < S; j0 += CH) {
+        EcdfCursor q[CH];
+        int top = 0;
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (j0 + k < S) { ecdf_top_search(e[j0 + k], s_top, rho[j0 + k], q[k]); top = e[j0 + k].nlev > top ? e[j0 + k].nlev : top; }
+        for (int lv = top - 2; lv >= 0; --lv) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k)
+                if (j0 + k < S && lv <= e[j0 + k].nlev - 2 && q[k].lb > 0) ecdf_descend(e[j0 + k], lv, q[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (j0 + k < S) u[j0 + k] = ecdf_finish(e[j0 + k], q[k]);
+    }
 }
 #endif
 
@@ -389,10 +430,13 @@ struct GaussSample {
 };
 
 // C3: stochastic logistic growth, θ = (r, K, σ), T = 20 points.  par: x0, T, obs[T]
+#ifndef SABC_LOGISTIC_SIM_MIN_BLOCKS
+#define SABC_LOGISTIC_SIM_MIN_BLOCKS 4   // 64 registers: 4 CTAs per SM hide the latency of the 20 ECDF lookups (1 / 2 / 3 / 4 / 5 CTAs: 1.07 / 0.65 / 0.50 / 0.47 / 0.70 ms per half-sweep)
+#endif
 struct Logistic {
     static constexpr int D = 3, S = 20;
     static constexpr int FUSED_MIN_BLOCKS = 1;
-    static constexpr int SIM_MIN_BLOCKS = 1;   // resident CTAs per SM requested for the simulation kernel
+    static constexpr int SIM_MIN_BLOCKS = SABC_LOGISTIC_SIM_MIN_BLOCKS;   // resident CTAs per SM requested for the simulation kernel
     static constexpr int KEY_BITS = 0;         // no work-list bucketing
     SABC_HD static void sim(const double (&th)[3], const ModelPar& mp, Stream& st, double (&rho)[20]) {
         double x = mp.v[0];
