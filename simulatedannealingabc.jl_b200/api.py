@@ -263,10 +263,22 @@ class SABCresult:
 SABCresult.ρ = property(lambda self: self.rho)
 
 
-def _require_device_model(f_dist):
-    if not isinstance(f_dist, DeviceModel):
-        raise TypeError("f_dist must be a DeviceModel (sabc_b200.models.*): arbitrary closures stay on the reference's CPU "
-                        "path (SimulatedAnnealingABC.jl); this package has no CPU fallback")
+def _resolve_model(f_dist, args, kwargs) -> DeviceModel:
+    """`f_dist(θ, args...; kwargs...)` of the reference (src/SimulatedAnnealingABC.jl:163,174,315,421): the extra arguments are the data
+    the closure works on.  On the device they are the model's parameter blob, so `f_dist` is either a DeviceModel (data already bound,
+    no extra arguments) or a device-model FACTORY (`sabc_b200.models.gauss_mean`, ...) that the extra arguments are passed to:
+    `sabc(sb.models.gauss_mean, prior, 1.0; sigma=1.0)`.  Arbitrary closures stay on the reference's CPU path."""
+    if isinstance(f_dist, DeviceModel):
+        if args or kwargs:
+            raise TypeError("this DeviceModel already holds its data: pass the factory (e.g. sabc_b200.models.gauss_mean) to have extra "
+                            "f_dist arguments bound into the parameter blob")
+        return f_dist
+    if callable(f_dist) and getattr(f_dist, "__module__", "").endswith(".models"):
+        m = f_dist(*args, **kwargs)
+        if isinstance(m, DeviceModel):
+            return m
+    raise TypeError("f_dist must be a DeviceModel or a device-model factory (sabc_b200.models.*): arbitrary closures stay on the "
+                    "reference's CPU path (SimulatedAnnealingABC.jl); this package has no CPU fallback")
 
 
 def _distributed_setup(comm):
@@ -303,9 +315,7 @@ def sabc(f_dist, prior: Distribution, *args, n_particles: int = 100, n_simulatio
     algorithm = str(algorithm).lstrip(":")
     if algorithm not in ALGORITHMS:                                                   # :462-464
         raise RuntimeError(f"Argument `algorithm` must be :multi_eps or :single_eps, not `{algorithm}`!")
-    _require_device_model(f_dist)
-    if args or kwargs:
-        raise TypeError("extra f_dist arguments are part of the DeviceModel parameter blob on the device path")
+    f_dist = _resolve_model(f_dist, args, kwargs)
     if n_simulation < n_particles:                                                    # :155-156
         raise RuntimeError(f"`n_simulation = {n_simulation}` is too small for {n_particles} particles.")
     if proposal is None:
@@ -333,7 +343,7 @@ def update_population(population_state: SABCresult, f_dist, prior: Distribution,
     Mutates and returns `population_state`."""
     if "δ" in kwargs:
         delta = kwargs.pop("δ")
-    _require_device_model(f_dist)
+    f_dist = _resolve_model(f_dist, args, kwargs)
     if v <= 0:
         raise RuntimeError("Annealing speed `v` must be positive.")                   # :261
     if delta <= 0:

@@ -13,7 +13,10 @@ int orc_model_simulate(int32_t model_id, int32_t d, int32_t s, const double* mod
 int64_t orc_poisson(double lam, uint64_t seed, uint32_t particle, uint64_t sweep, uint32_t* block_io);
 void orc_prior_rand(int32_t d, const int32_t* kind, const double* par, uint64_t seed, uint32_t particle, double* theta_out);
 double orc_prior_logpdf(int32_t d, const int32_t* kind, const double* par, const double* theta);
+int orc_propose(int32_t proposal, const double* pp, int32_t d, const double* th, const double* P, int64_t M, const double* chol, uint64_t seed,
+                uint32_t particle, uint64_t sweep, double* out, double* lf);
 }
+struct RowMajor { const double* p; int d; double operator()(int c, int64_t i) const { return p[i * d + c]; } };
 using namespace sabc;
 
 int main(int argc, char** argv) {
@@ -49,6 +52,46 @@ int main(int argc, char** argv) {
         SirTauLeap::sim(thr, mp, st, rho);
         orc_model_simulate(3, 4, 3, par, 6, th, 77, (uint32_t)i, 5, ro);
         if (memcmp(rho, ro, sizeof rho) != 0) { if (bad < 10) printf("sir mismatch %d\n", i); bad++; }
+    }
+    // ziggurat normals through the models that draw them (Gaussian mean, Gaussian sample, logistic growth) and through the DE / RandomWalk
+    // proposals: fast path, wedge and tail of the sampler on the host build of the product headers against the oracle
+    {
+        const double pg[2] = {1.0, 0.31622776601683794}, ps[5] = {10, 1.0, 2.0, 42.5, 1.0};
+        double pl[22] = {10.0, 20.0};
+        for (int t = 0; t < 20; ++t) pl[2 + t] = 15.0 + 11.0 * t;
+        ModelPar mg{}, ms{}, ml{};
+        for (int i = 0; i < 2; ++i) mg.v[i] = pg[i];
+        for (int i = 0; i < 5; ++i) ms.v[i] = ps[i];
+        for (int i = 0; i < 22; ++i) ml.v[i] = pl[i];
+        const int n_norm = 60 * n_sim;
+        for (int i = 0; i < n_norm; ++i) {
+            Stream r(321, (uint32_t)i, 0, KIND_PRIOR);
+            const U64x2 a = r.draw(), b = r.draw();
+            { double th[1] = {4.0 * u53(a.a) - 2.0}, rho[1], ro[1]; Stream st(55, (uint32_t)i, 9, KIND_MODEL); const double(&t1)[1] = th;
+              GaussMean::sim(t1, mg, st, rho); orc_model_simulate(0, 1, 1, pg, 2, th, 55, (uint32_t)i, 9, ro);
+              if (memcmp(rho, ro, sizeof rho) != 0) { if (bad < 10) printf("gauss_mean mismatch %d\n", i); bad++; } }
+            { double th[2] = {6.0 * u53(a.a) - 3.0, 0.1 + 2.0 * u53(a.b)}, rho[2], ro[2]; Stream st(55, (uint32_t)i, 9, KIND_MODEL); const double(&t2)[2] = th;
+              GaussSample<2, 2>::sim(t2, ms, st, rho); orc_model_simulate(1, 2, 2, ps, 5, th, 55, (uint32_t)i, 9, ro);
+              if (memcmp(rho, ro, sizeof rho) != 0) { if (bad < 10) printf("gauss_sample mismatch %d\n", i); bad++; } }
+            if (i % 4 == 0) { double th[3] = {u53(a.a), 50.0 + 450.0 * u53(a.b), 0.5 * u53(b.a)}, rho[20], ro[20]; Stream st(55, (uint32_t)i, 9, KIND_MODEL);
+              const double(&t3)[3] = th;
+              Logistic::sim(t3, ml, st, rho); orc_model_simulate(2, 3, 20, pl, 22, th, 55, (uint32_t)i, 9, ro);
+              if (memcmp(rho, ro, sizeof rho) != 0) { if (bad < 10) printf("logistic mismatch %d\n", i); bad++; } }
+            if (i % 8 == 0) {                       // proposals over a small inactive half
+                double P[16 * 3], th[3] = {u53(a.a), u53(a.b), u53(b.a)}, out[3], oo[3], lf, lo;
+                for (int k = 0; k < 48; ++k) P[k] = u53(Stream(7, (uint32_t)k, 0, KIND_PRIOR).block(0).a);
+                const double pp[2] = {2.38 / sqrt(6.0), 1e-5}, chol[9] = {0.5, 0, 0, 0.1, 0.4, 0, -0.2, 0.05, 0.3};
+                const double(&t3)[3] = th; double(&o3)[3] = out;
+                const CtrlWords cw = ctrl_words(99, (uint32_t)i, 4);
+                propose_de<3>(t3, RowMajor{P, 3}, 16, pp[0], pp[1], cw, Stream(99, (uint32_t)i, 4, KIND_CTRL), o3, lf);
+                orc_propose(0, pp, 3, th, P, 16, chol, 99, (uint32_t)i, 4, oo, &lo);
+                if (memcmp(out, oo, sizeof out) != 0 || lf != lo) { if (bad < 10) printf("propose_de mismatch %d\n", i); bad++; }
+                propose_rw<3>(t3, chol, 99, (uint32_t)i, 4, o3, lf);
+                orc_propose(2, pp, 3, th, P, 16, chol, 99, (uint32_t)i, 4, oo, &lo);
+                if (memcmp(out, oo, sizeof out) != 0 || lf != lo) { if (bad < 10) printf("propose_rw mismatch %d\n", i); bad++; }
+            }
+        }
+        printf("%d gaussian / logistic simulations and proposals checked\n", n_norm);
     }
     // priors: every family, draws and log-densities (also off the support)
     const int n_prior = 20000;

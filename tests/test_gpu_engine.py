@@ -248,6 +248,10 @@ def test_public_api_counters(gpu):
         res = sb.sabc(f2, p2, proposal=p, n_particles=100, n_simulation=1000)
         sb.update_population(res, f2, p2, proposal=p, n_simulation=1000)
         assert res.state.n_simulation <= 2000
+    # f_dist(θ, args...; kwargs...): the extra arguments are bound into the device model (factory as f_dist)
+    ra = sb.sabc(sb.models.gauss_sample, p2, 10, 2.0, 42.5, n_para=2, second_is_sum=True, n_particles=100, n_simulation=1000, algorithm="multi_eps")
+    rb = sb.sabc(f2, p2, n_particles=100, n_simulation=1000, algorithm="multi_eps")
+    assert np.array_equal(ra.population, rb.population) and np.array_equal(ra.state.eps, rb.state.eps)
     with pytest.raises(RuntimeError):
         sb.update_population(res, f2, p2, n_simulation=1000, v=-0.1)
     with pytest.raises(RuntimeError):

@@ -83,6 +83,23 @@ def test_argument_validation_before_any_device_work():
         sb.sabc(model, prior, n_particles=100, n_simulation=1000, type="triple")
 
 
+def test_extra_f_dist_arguments_bind_into_the_model():
+    """f_dist(θ, args...; kwargs...) (:163,174,315,421): with a device-model factory as f_dist the extra arguments of sabc() /
+    update_population!() become the model's data, exactly what a closure over them would have captured."""
+    from sabc_b200.api import _resolve_model
+    m = _resolve_model(sb.models.gauss_mean, (1.0,), {"sigma": 2.0, "n_obs": 4})
+    assert isinstance(m, sb.DeviceModel) and m.name == "gauss_mean" and np.array_equal(m.par, [1.0, 1.0])
+    m2 = _resolve_model(sb.models.gauss_sample, (10, 2.0, 42.5), {"n_para": 2, "second_is_sum": True})
+    assert m2.name == "gauss_sample_d2s2" and (m2.n_para, m2.n_stats) == (2, 2)
+    assert _resolve_model(m, (), {}) is m
+    with pytest.raises(TypeError, match="already holds its data"):
+        _resolve_model(m, (3.0,), {})
+    with pytest.raises(TypeError, match="closures"):
+        _resolve_model(lambda th, y: abs(th - y), (1.0,), {})
+    with pytest.raises(TypeError):                                          # a factory called with arguments it does not take
+        _resolve_model(sb.models.gauss_mean, (), {"not_a_parameter": 1})
+
+
 def test_config_validation_in_the_library():
     L = sb._lib
     model, prior = sb.models.gauss_mean(1.0), sb.Normal(0, 1)
