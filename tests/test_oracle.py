@@ -314,3 +314,29 @@ def test_pin_against_the_real_reference_if_it_is_runnable():
         k = o_ecdf_build(np.array(data))
         mine = o_ecdf_eval(k, np.array([2.0, 2.5, 3.0, np.inf, 0.0]))
         assert np.array_equal(mine, np.array(want)), (mine, want)
+
+
+def test_ziggurat_normal_is_standard_normal():
+    """the hot path's randn(): 256-layer ziggurat on one Philox word.  Distribution (KS), moments, the share of
+    draws that need the slow path (1.5 %: wedges and tail) and the tail beyond R = 3.654 against the normal law."""
+    from scipy import stats
+    n = 400_000
+    z = np.empty(n); blocks = 0
+    b = C.c_uint32(0)
+    for i in range(n):
+        b.value = 0
+        z[i] = ob.lib().orc_zig_normal(12345, i, 7, C.byref(b)); blocks += b.value
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    assert abs(z.mean()) < 4 / np.sqrt(n) and abs(z.var() - 1) < 4 * np.sqrt(2 / n)
+    assert abs(stats.skew(z)) < 0.02 and abs(stats.kurtosis(z)) < 0.04
+    assert 1.010 < blocks / n < 1.020                                   # one block per draw + ~1.5 % slow paths
+    R = 3.6541528853610088
+    tail = (np.abs(z) > R).sum(); want = 2 * stats.norm.sf(R) * n
+    assert abs(tail - want) < 5 * np.sqrt(want), (tail, want)
+    for q in (0.5, 1.0, 2.0, 3.0):
+        k = (np.abs(z) > q).sum(); w = 2 * stats.norm.sf(q) * n
+        assert abs(k - w) < 5 * np.sqrt(w), (q, k, w)
+    # two streams never share draws; the same (seed, particle, sweep) always gives the same normal
+    b.value = 0; a1 = ob.lib().orc_zig_normal(12345, 5, 7, C.byref(b))
+    b.value = 0; a2 = ob.lib().orc_zig_normal(12345, 5, 7, C.byref(b))
+    assert a1 == a2 == z[5]
