@@ -130,7 +130,7 @@ SABC_HD void det_sincos2pi(double u, double& sn, double& cs) {
     cs = (qq == 0) ? cr : (qq == 1) ? -sr : (qq == 2) ? -cr : sr;
 }
 
-// cos(2 pi u) only (DE jitter, first Box-Muller output)
+// cos(2 pi u) only
 SABC_HD double det_cos2pi(double u) {
     double s, c; det_sincos2pi(u, s, c); return c;
 }

@@ -1,11 +1,13 @@
-// multi_gpu.inl -- one process per GPU, contiguous particle slices.  Included by engine.cu.
+// multi_gpu.inl -- ranks of one communicator, contiguous particle slices.  Included by engine.cu.  A rank is a
+// process (one per GPU) or one of the per-GPU engines of a single-process handle (group.inl): the code below is the same.
 //
-// Per population update only the tiny reductions cross NVLink: one integer all-reduce of the exact
-// Σu limbs + accept count and one FP64 all-reduce of the ρ sums; every rank then solves ε
-// redundantly.  DE/Stretch partners come from the rank's own inactive half.  Resampling is the exact
-// global multinomial of the reference (:129): all ranks draw the same N global variates, each keeps
-// the draws that land in its weight range and ships only the surplus to the ranks that own the
-// destination slots (grouped ncclSend/ncclRecv).
+// Per population update ONE collective crosses NVLink: an all-gather of every rank's packed statistics (exact Σu limbs, accept
+// count, FP64 ρ sums), reduced in rank order on every rank, which then solves ε redundantly.  The update sequence is enqueued
+// without host round trips (look-ahead with a device-side `hold` flag, replayed as a CUDA graph).  DE/Stretch partners come from
+// the rank's own inactive half.  Resampling is the exact global multinomial of the reference (:129), split by rank: the per-rank
+// counts are one multinomial draw from a shared seed, each rank draws its particles locally and ships only the surplus to the
+// ranks that own the destination slots (grouped ncclSend/ncclRecv).  The strict variant (all ranks walk the same N global
+// variates; multiset equal to one GPU's) and the replicated mode (bit-identical to one GPU) are the parity instruments.
 
 static __global__ void __launch_bounds__(CHUNK) k_mg_mark(int64_t n_global, unsigned long long w_total, unsigned long long my_off,
                                                    unsigned long long my_w, const unsigned long long* P, int64_t n_local,
