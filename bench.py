@@ -168,13 +168,18 @@ def cpu_oracle_throughput(model, prior, algorithm, *, target_seconds: float, ste
 
 
 def csrc_digest() -> str:
-    """sha256 over the CUDA sources: stamps the committed ncu counts, so that a number taken from an older kernel is never reported."""
+    """sha256 over the CUDA sources with comments and white space removed: stamps the committed ncu counts, so that a number taken
+    from an older kernel is never reported (and an edited comment does not invalidate it)."""
     import hashlib
+    import re
     h = hashlib.sha256()
     d = os.path.join(ROOT, "simulatedannealingabc.jl_b200", "csrc")
     for f in sorted(os.listdir(d)):
         if f.endswith((".cu", ".cuh", ".inl", ".h")):
-            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+            text = open(os.path.join(d, f), errors="replace").read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            text = re.sub(r"//[^\n]*", "", text)
+            h.update(f.encode()); h.update(re.sub(r"\s+", "", text).encode())
     return h.hexdigest()[:16]
 
 
