@@ -363,16 +363,16 @@ static int mg_enqueue_iteration(sabc_engine* e) {
     SABC_TRY(launch_finish(e));
     return 0;
 }
-// the host half of an update whose decision raised `hold`: the global resampling, then the rest of that update
+// the host half of an update whose decision raised `hold`: the global resampling, then the rest of that update.  Everything is
+// stream-ordered behind the squashed updates; the only host wait is the one inside mg_resample (the per-rank weight totals the
+// multinomial split needs), so the next updates are enqueued while the exchange is still running.
 static int mg_complete_held_iteration(sabc_engine* e) {
     const auto t0 = std::chrono::steady_clock::now();
-    SABC_CUDA(cudaStreamSynchronize(e->stream));
     SABC_TRY(mg_resample(e));
     k_mg_release<<<1, 1, 0, e->stream>>>(e->b_ds.p);
     SABC_CUDA(cudaGetLastError());
     SABC_TRY(launch_update_proposal_mg(e));
     SABC_TRY(launch_finish(e));
-    SABC_CUDA(cudaStreamSynchronize(e->stream));
     e->timing.resample_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     e->timing.resample_events += 1;
     return 0;
