@@ -1,12 +1,14 @@
 /* Plain-C host of the C ABI (what a Julia `ccall` or any FFI does): C1 = 1-D Gaussian mean, N = 1000, n_simulation = 100000.
  *   gcc -O2 -I include examples/c_host/sabc_c_host.c -o sabc_c_host -L simulatedannealingabc.jl_b200 -l:libsabc_b200.so \
  *       -Wl,-rpath,$PWD/simulatedannealingabc.jl_b200
- * Exit code 0 and one line "ok ..." on success; on a box without a CUDA device it prints the library's error and exits 3. */
+ * Exit code 0 and one line "ok ..." on success; on a box without a CUDA device it prints the library's error and exits 3.
+ * `sabc_c_host G` (G > 1): the same call sequence with cfg.n_gpus = G -- this one process drives G GPUs through the one handle, the
+ * arrays it reads back are the global ones. */
 #include <stdio.h>
 #include <stdlib.h>
 #include "sabc_b200.h"
 
-int main(void) {
+int main(int argc, char** argv) {
     const double model_par[2] = {1.0, 0.31622776601683794};       /* ybar_obs, sigma/sqrt(n) */
     const int32_t prior_kind[1] = {SABC_PRIOR_NORMAL};
     const double prior_par[2] = {0.0, 1.0};
@@ -17,6 +19,7 @@ int main(void) {
     cfg.v = 1.0; cfg.delta = 0.1; cfg.resample = 1000; cfg.seed = 0x5ABC;   /* the configuration of tests/golden/trajectories.json[0] */
     cfg.model_name = "gauss_mean"; cfg.model_par = model_par; cfg.n_model_par = 2; cfg.device = -1;
     cfg.prior_kind = prior_kind; cfg.prior_par = prior_par; cfg.rank = 0; cfg.world_size = 1;
+    cfg.n_gpus = argc > 1 ? atoi(argv[1]) : 0; cfg.gpu_ids = NULL;         /* ABI 2: single-process multi-GPU handle */
 
     sabc_engine* e = NULL;
     int rc = sabc_create(&e, &cfg);

@@ -42,3 +42,20 @@ def test_c_host_reproduces_c1_fixture(gpu, c_host):
     got = [int(out[k]) for k in ("n_simulation", "n_accept", "n_resampling", "n_population_updates")]
     assert got == fx["counters"] and int(out["records"]) == len(fx["eps_history"])
     assert float.fromhex(out["eps"]) == float.fromhex(fx["eps"][0])              # bit-identical to the oracle-made fixture
+
+
+@pytest.mark.gpu
+def test_c_host_drives_two_gpus_through_one_handle(gpu, c_host):
+    """cfg.n_gpus = 2 from plain C: same counters semantics, a finite posterior sample over the global array (the sharded run is not
+    bit-comparable with the one-GPU fixture: partners come from the local halves)."""
+    import ctypes as C
+    import sabc_b200 as sb
+    n = C.c_int(0)
+    sb._lib.lib().sabc_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([c_host, "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = dict(kv.split("=") for kv in r.stdout.split()[1:])
+    assert int(out["n_simulation"]) == 100000 and int(out["n_population_updates"]) == 99 and int(out["n_resampling"]) >= 2
+    assert 0.7 < float(out["mean"]) < 1.1 and 0 < float.fromhex(out["eps"]) < 0.05
