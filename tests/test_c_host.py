@@ -56,6 +56,7 @@ def test_c_host_drives_two_gpus_through_one_handle(gpu, c_host):
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([c_host, "2"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    out = dict(kv.split("=") for kv in r.stdout.split()[1:])
+    line = [l for l in r.stdout.splitlines() if l.startswith("ok ")][0]     # NCCL prints its version banner on stdout as well
+    out = dict(kv.split("=") for kv in line.split()[1:])
     assert int(out["n_simulation"]) == 100000 and int(out["n_population_updates"]) == 99 and int(out["n_resampling"]) >= 2
     assert 0.7 < float(out["mean"]) < 1.1 and 0 < float.fromhex(out["eps"]) < 0.05
