@@ -58,6 +58,42 @@ sl = slice(rank * n_local, (rank + 1) * n_local)
 t = torch.tensor([hi[sl].sum(), lo[sl].sum()], dtype=torch.int64)
 dist.all_reduce(t)
 assert int(t[0]) == int(hi.sum()) and int(t[1]) == int(lo.sum())
+# 4. the sharded resampling's host half, as multi_gpu.inl runs it: every rank all-gathers the per-rank weight totals, computes the
+#    multinomial split of the N draws on its own (same seed, same resampling count -> same counts, or the exchange would
+#    dead-lock), packs c_me "selected particles" and runs the surplus exchange of the plan; every rank must end with a full slice
+rng = np.random.default_rng(5 + rank)
+for rc in range(4):
+    w_me = int(rng.integers(2**35, 2**40)) if not (rc == 3 and rank == 0) else 0      # last round: one rank weighs nothing
+    ws = [None] * world
+    dist.all_gather_object(ws, w_me)
+    w = np.array(ws, dtype=np.uint64)
+    counts = np.zeros(world, dtype=np.int64)
+    assert sb._lib.lib().sabc_multinomial_split(n_local * world, sb._lib.ptr(w), world, 0x5ABC, rc, sb._lib.ptr(counts)) == 0
+    allc = [None] * world
+    dist.all_gather_object(allc, counts.tolist())
+    assert all(c == allc[0] for c in allc) and sum(allc[0]) == n_local * world
+    if w_me == 0:
+        assert counts[rank] == 0
+    C0 = int(counts[:rank].sum())
+    mine = np.arange(C0, C0 + counts[rank], dtype=np.float64)                         # payload = global slot of the selection
+    arrs = [np.zeros(world, dtype=np.int64) for _ in range(4)]
+    assert sb._lib.lib().sabc_mg_exchange_plan(sb._lib.ptr(counts), world, n_local, rank, *[sb._lib.ptr(a) for a in arrs]) == 0
+    s_off, s_cnt, r_off, r_cnt = arrs
+    out = np.full(n_local, np.nan)
+    out[r_off[rank]:r_off[rank] + r_cnt[rank]] = mine[s_off[rank]:s_off[rank] + s_cnt[rank]]
+    reqs, bufs = [], {}
+    for g in range(world):
+        if g != rank and r_cnt[g] > 0:
+            bufs[g] = torch.empty(int(r_cnt[g]), dtype=torch.float64); reqs.append(dist.irecv(bufs[g], src=g))
+    for d in range(world):
+        if d != rank and s_cnt[d] > 0:
+            reqs.append(dist.isend(torch.from_numpy(mine[s_off[d]:s_off[d] + s_cnt[d]].copy()), dst=d))
+    for q in reqs:
+        q.wait()
+    for g, b in bufs.items():
+        out[r_off[g]:r_off[g] + r_cnt[g]] = b.numpy()
+    assert np.array_equal(out, np.arange(rank * n_local, (rank + 1) * n_local, dtype=np.float64)), (rank, rc)
+    dist.barrier()
 dist.destroy_process_group()
 print("OK", rank)
 '''
