@@ -89,3 +89,60 @@ def test_ctypes_mirrors_match_the_header(tmp_path):
             d = getattr(mirror, f)
             assert (d.offset, d.size) == c[f], (struct, f)
         assert C.sizeof(mirror) == c["__size__"][0]
+
+
+def _split_top(s):
+    """split a comma list at nesting depth 0 ({...} and (...) may contain commas)"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "{(":
+            depth += 1
+        if ch in "})":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_ccall_signatures_match_the_header():
+    """every `ccall((:sabc_x, libsabc), Ret, (T1, T2, ...), ...)` of SABCB200.jl against the prototype of sabc_x in the header: same
+    number of arguments, and argument by argument the same class (pointer / 64-bit integer / 32-bit integer / double)."""
+    hdr = open(os.path.join(ROOT, "include", "sabc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(sabc_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if args == ["void"] else args
+
+    def c_class(a):
+        if "*" in a or "[" in a:
+            return "ptr"
+        t = a.split()
+        ty = " ".join(t[:-1]) if len(t) > 1 else t[0]
+        return {"int64_t": "i64", "uint64_t": "i64", "int32_t": "i32", "uint32_t": "i32", "int": "i32", "double": "f64"}[ty.replace("const ", "")]
+
+    def jl_class(t):
+        if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+            return "ptr"
+        return {"Int64": "i64", "UInt64": "i64", "Int32": "i32", "UInt32": "i32", "Cint": "i32", "Float64": "f64"}[t]
+
+    text = open(JL).read()
+    seen = set()
+    for m in re.finditer(r"ccall\(\(:(sabc_\w+), libsabc\),\s*(\w+),\s*\(", text):
+        name = m.group(1)
+        depth, i = 1, m.end()
+        while depth:                                    # the matching parenthesis of the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(text[i], 0); i += 1
+        types = [t for t in _split_top(text[m.end():i - 1]) if t]
+        assert name in protos, f"{name} is not declared in the header"
+        want = protos[name]
+        assert len(types) == len(want), f"{name}: julia passes {len(types)} arguments, the header declares {len(want)}"
+        for k, (jt, ca) in enumerate(zip(types, want)):
+            assert jl_class(jt) == c_class(ca), f"{name} argument {k + 1}: julia {jt} vs C `{ca}`"
+        seen.add(name)
+    assert {"sabc_create", "sabc_init", "sabc_update", "sabc_update_host", "sabc_set_tuning", "sabc_get_population", "sabc_get_state",
+            "sabc_get_history", "sabc_history_len", "sabc_destroy", "sabc_last_error"} <= seen
