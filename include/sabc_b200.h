@@ -68,7 +68,7 @@ typedef struct sabc_config {
     int32_t  device;          /* CUDA device ordinal; -1 = current device */
     const int32_t* prior_kind;/* n_para entries, SABC_PRIOR_* */
     const double*  prior_par; /* 2*n_para entries: Uniform (a,b) | Normal (mu,sigma) | Exponential (theta,0) | LogNormal (mu,sigma) | Gamma (alpha,theta) | Beta (alpha,beta) | Cauchy (mu,sigma) | Laplace (mu,theta) | Weibull (alpha,theta) | InverseGamma (alpha,theta) */
-    /* multi-GPU: one process per GPU, this rank owns a contiguous slice of n_particles/world_size */
+    /* multi-GPU, one process per GPU: this rank owns a contiguous slice of n_particles/world_size (one process for all GPUs: n_gpus below) */
     int32_t  rank, world_size;
     const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; NULL when world_size == 1 */
     uint32_t flags;           /* SABC_FLAG_* */
@@ -89,9 +89,9 @@ typedef struct sabc_config {
 #define SABC_FLAG_NO_PIPELINE   8u  /* sabc_update_host: upload, update, download strictly one after the other */
 #define SABC_FLAG_SORT_WORK    16u  /* split path: bucket the work list by the model's similarity key (if it has one) */
 #define SABC_FLAG_GENERIC_TAIL 32u  /* never use the single-CTA tail kernel of small populations */
-#define SABC_FLAG_MG_REPLICATED 64u /* world_size > 1: every rank holds the whole population and simulates a share of each half-sweep;
+#define SABC_FLAG_MG_REPLICATED 64u /* world_size > 1 or n_gpus > 1: every rank holds the whole population and simulates a share of each half-sweep;
                                        bit-identical to one GPU (strict mode for parity studies, memory does not scale) */
-#define SABC_FLAG_MG_STRICT_RESAMPLE 128u /* world_size > 1, sharded: every rank walks all N global resampling draws, so that the resampled
+#define SABC_FLAG_MG_STRICT_RESAMPLE 128u /* world_size > 1 or n_gpus > 1, sharded: every rank walks all N global resampling draws, so that the resampled
                                        multiset equals the single-GPU one for the same seed (O(N_global) work and memory per rank);
                                        default: per-rank counts from ONE shared-seed multinomial draw, O(N / world_size) per rank */
 #define SABC_FLAG_FUSED         4u  /* always use the fused update_half kernel, also for simulation-heavy models */
@@ -125,7 +125,8 @@ int  sabc_init(sabc_engine* e);
 int  sabc_update(sabc_engine* e, int64_t n_simulation, int64_t checkpoint_history);
 /* same call with the SABCresult held in HOST buffers, as Julia's update_population!(::SABCresult)
  * would make it: uploads (theta,u,rho,eps,counters), runs the updates, downloads the result into the
- * same buffers.  This rank's slice only when world_size > 1. */
+ * same buffers.  world_size > 1: this rank's slice (n_particles / world_size rows).  n_gpus > 1: the GLOBAL arrays (leading
+ * dimension n_particles); every GPU of the handle copies its own rows. */
 int  sabc_update_host(sabc_engine* e, double* theta, double* u, double* rho, double* eps, int64_t counters[4],
                       int64_t n_simulation, int64_t checkpoint_history);
 
